@@ -1,0 +1,136 @@
+// K5: classifier + softmax cross-entropy, forward and backward in two launches.
+// Replaces `scores = self.weight.mm(embeds).t()` and nn.CrossEntropyLoss()(scores, labels)
+// (graphsage/model.py:57, 62-69) and their autograd backward (model.py:249).
+#include "gs_common.cuh"
+
+namespace {
+
+constexpr int kRowsPerBlock = 8;      // one warp per target row
+constexpr int kMaxClsPerLane = 4;     // num_classes <= 128
+
+// ws layout: dl[n, C] (scaled softmax - onehot), then loss_i[n]
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+xent_rows_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restrict__ wc, int64_t ld_wc,
+                 const int64_t* __restrict__ labels, int d, int C, int n, float gscale,
+                 float* __restrict__ logits, int64_t ld_logits, float* __restrict__ gh, int64_t ld_gh,
+                 float* __restrict__ ws) {
+    extern __shared__ float smem[];
+    float* s_wc = smem;                               // [C][d+1]  (stride d+1: conflict-free per-class reads)
+    float* s_h = smem + (size_t)C * (d + 1);          // [rows][d]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < C * d; e += blockDim.x) {
+        const int c = e / d, k = e - c * d;
+        s_wc[c * (d + 1) + k] = wc[(int64_t)c * ld_wc + k];
+    }
+    const int row = blockIdx.x * kRowsPerBlock + w;
+    float* hrow = s_h + w * d;
+    if (row < n)
+        for (int k = lane; k < d; k += 32) hrow[k] = h[(int64_t)row * ld_h + k];
+    __syncthreads();
+    if (row >= n) return;
+
+    float z[kMaxClsPerLane];
+    float zmax = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < kMaxClsPerLane; ++q) {
+        const int c = lane + 32 * q;
+        float acc = 0.f;
+        if (c < C) {
+            const float* wr = s_wc + c * (d + 1);
+            for (int k = 0; k < d; ++k) acc = fmaf(hrow[k], wr[k], acc);
+            zmax = fmaxf(zmax, acc);
+            if (logits) logits[(int64_t)row * ld_logits + c] = acc;
+        }
+        z[q] = acc;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxClsPerLane; ++q)
+        if (lane + 32 * q < C) sum += expf(z[q] - zmax);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float lse = zmax + logf(sum);
+    const int y = (int)labels[row];
+    float dl[kMaxClsPerLane];
+    float picked = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxClsPerLane; ++q) {
+        const int c = lane + 32 * q;
+        dl[q] = 0.f;
+        if (c < C) {
+            const float p = expf(z[q] - lse);
+            dl[q] = (p - (c == y ? 1.f : 0.f)) * gscale;
+            if (c == y) picked = z[q];
+            ws[(int64_t)row * C + c] = dl[q];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) picked += __shfl_xor_sync(0xffffffffu, picked, o);
+    if (lane == 0) ws[(int64_t)n * C + row] = lse - picked;
+    if (gh != nullptr) {
+        for (int k = lane; k < d; k += 32) {
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < kMaxClsPerLane; ++q)
+                for (int l = 0; l < 32; ++l) {
+                    const int c = l + 32 * q;
+                    if (c >= C) break;
+                    acc = fmaf(__shfl_sync(0xffffffffu, dl[q], l), s_wc[c * (d + 1) + k], acc);
+                }
+            gh[(int64_t)row * ld_gh + k] = acc;
+        }
+    }
+}
+
+// gwc[c, :] = sum_i dl[i, c] * h[i, :]   (block per class, fixed order over i);
+// block 0 also reduces the per-row losses to the mean.
+__global__ void __launch_bounds__(256)
+xent_wgrad_kernel(const float* __restrict__ h, int64_t ld_h, int d, int C, int n,
+                  const float* __restrict__ ws, float* __restrict__ gwc, int64_t ld_gwc, float* __restrict__ loss) {
+    const int c = blockIdx.x;
+    if (gwc != nullptr) {
+        for (int k = threadIdx.x; k < d; k += blockDim.x) {
+            float acc = 0.f;
+            for (int i = 0; i < n; ++i) acc = fmaf(ws[(int64_t)i * C + c], h[(int64_t)i * ld_h + k], acc);
+            gwc[(int64_t)c * ld_gwc + k] = acc;
+        }
+    }
+    if (c == 0 && loss != nullptr) {
+        __shared__ float part[256];
+        float s = 0.f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s += ws[(int64_t)n * C + i];
+        part[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o; o >>= 1) {
+            if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) loss[0] = part[0] / (float)n;
+    }
+}
+
+}  // namespace
+
+extern "C" int gs_classifier_xent(const float* h, int64_t ld_h, const float* wc, int64_t ld_wc,
+                                  const int64_t* labels, int32_t d, int32_t num_classes, int32_t n,
+                                  float grad_scale, float* logits, int64_t ld_logits, float* loss,
+                                  float* gh, int64_t ld_gh, float* gwc, int64_t ld_gwc,
+                                  float* ws, void* stream) {
+    if (!h || !wc || !labels || !ws || d <= 0 || num_classes <= 0 || n <= 0) return GS_EINVAL;
+    if (num_classes > 32 * kMaxClsPerLane) return GS_ENOSUP;
+    const size_t smem = ((size_t)num_classes * (d + 1) + (size_t)kRowsPerBlock * d) * sizeof(float);
+    if (smem > 200 * 1024) return GS_ENOSUP;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(xent_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    xent_rows_kernel<<<(n + kRowsPerBlock - 1) / kRowsPerBlock, kRowsPerBlock * 32, smem, s>>>(
+        h, ld_h, wc, ld_wc, labels, d, num_classes, n, grad_scale / (float)n, logits, ld_logits, gh, ld_gh, ws);
+    GS_LAUNCH_CHECK();
+    xent_wgrad_kernel<<<num_classes, 256, 0, s>>>(h, ld_h, d, num_classes, n, ws, gwc, ld_gwc, loss);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}

@@ -1,0 +1,241 @@
+// K2 gather-mean forward, K4 scatter-add backward, row gather, SGD.
+// Replaces graphsage/aggregators.py:54-65,74 (dense mask + mask.mm), encoders.py:49-54
+// (self lookup + cat), the autograd backward of mask.mm (model.py:249) and the SGD step
+// (model.py:250) of the reference.
+#include "gs_common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+// Load 4 consecutive floats of a row whose base is 16-B aligned; columns >= dim read as 0.
+__device__ __forceinline__ float4 load_chunk(const float* __restrict__ row, int c4, int dim) {
+    const int col = c4 * 4;
+    if (col + 4 <= dim) return gs_ldg_stream(reinterpret_cast<const float4*>(row) + c4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < dim) v.x = __ldg(row + col);
+    if (col + 1 < dim) v.y = __ldg(row + col + 1);
+    if (col + 2 < dim) v.z = __ldg(row + col + 2);
+    return v;
+}
+
+// Store 4 floats at dst (alignment `al` floats: 4, 2 or 1), only columns < dim.
+__device__ __forceinline__ void store_chunk(float* __restrict__ dst_row, int c4, int dim, int al, float4 v) {
+    const int col = c4 * 4;
+    float* d = dst_row + col;
+    if (col + 4 <= dim) {
+        if (al == 4) { *reinterpret_cast<float4*>(d) = v; }
+        else if (al == 2) {
+            *reinterpret_cast<float2*>(d) = make_float2(v.x, v.y);
+            *reinterpret_cast<float2*>(d + 2) = make_float2(v.z, v.w);
+        } else { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+    } else {
+        if (col < dim) d[0] = v.x;
+        if (col + 1 < dim) d[1] = v.y;
+        if (col + 2 < dim) d[2] = v.z;
+    }
+}
+
+// One warp per target row.  Lane l owns float4 chunks l, l+32, ... of the feature row, so a
+// warp-wide load is one contiguous 512-byte run of the neighbour's row (4 full 128-B lines).
+// CH chunks per lane are kept in registers and NB neighbours are in flight at once, i.e.
+// CH*NB independent 128-bit loads per lane, which is what hides HBM latency here.
+template <int CH, int NB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+gather_mean_kernel(const float* __restrict__ table, int64_t ld_table, int dim,
+                   const int32_t* __restrict__ idx, const int32_t* __restrict__ cnt, int width,
+                   const int32_t* __restrict__ self_ids, int n_max, const int32_t* __restrict__ n_dev,
+                   float* __restrict__ out, int64_t ld_out, int neigh_off, int out_align) {
+    const int n = gs_row_count(n_max, n_dev);
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int nchunks = (dim + 3) >> 2;
+    const int c = min(cnt[row], width);
+    const float inv = c > 0 ? 1.f / (float)c : 0.f;
+    float* orow = out + (int64_t)row * ld_out;
+    const int32_t* irow = idx + (int64_t)row * width;
+
+    if (self_ids != nullptr) {          // bit-exact copy of the node's own row (encoders.py:53)
+        const float* srow = table + (int64_t)self_ids[row] * ld_table;
+        for (int c4 = lane; c4 < nchunks; c4 += 32) store_chunk(orow, c4, dim, 4, load_chunk(srow, c4, dim));
+    }
+    for (int c0 = 0; c0 < nchunks; c0 += 32 * CH) {
+        float4 acc[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j0 = 0; j0 < c; j0 += 32) {
+            const int my = (j0 + lane < c) ? irow[j0 + lane] : 0;
+            const int lim = min(32, c - j0);
+            int j = 0;
+            for (; j + NB <= lim; j += NB) {
+                float4 v[NB][CH];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const float* nrow = table + (int64_t)__shfl_sync(0xffffffffu, my, j + b) * ld_table;
+#pragma unroll
+                    for (int u = 0; u < CH; ++u) {
+                        const int c4 = c0 + u * 32 + lane;
+                        v[b][u] = c4 < nchunks ? load_chunk(nrow, c4, dim) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+#pragma unroll
+                    for (int u = 0; u < CH; ++u) {
+                        acc[u].x += v[b][u].x; acc[u].y += v[b][u].y;
+                        acc[u].z += v[b][u].z; acc[u].w += v[b][u].w;
+                    }
+            }
+            for (; j < lim; ++j) {
+                const float* nrow = table + (int64_t)__shfl_sync(0xffffffffu, my, j) * ld_table;
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    const int c4 = c0 + u * 32 + lane;
+                    if (c4 < nchunks) {
+                        float4 t = load_chunk(nrow, c4, dim);
+                        acc[u].x += t.x; acc[u].y += t.y; acc[u].z += t.z; acc[u].w += t.w;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int c4 = c0 + u * 32 + lane;
+            if (c4 < nchunks) {
+                float4 m = make_float4(acc[u].x * inv, acc[u].y * inv, acc[u].z * inv, acc[u].w * inv);
+                store_chunk(orow + neigh_off, c4, dim, out_align, m);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+gather_rows_kernel(const float* __restrict__ table, int64_t ld_table, int dim,
+                   const int32_t* __restrict__ ids, int n_max, const int32_t* __restrict__ n_dev,
+                   float* __restrict__ out, int64_t ld_out) {
+    const int n = gs_row_count(n_max, n_dev);
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int nchunks = (dim + 3) >> 2;
+    const float* srow = table + (int64_t)ids[row] * ld_table;
+    float* orow = out + (int64_t)row * ld_out;
+    for (int c4 = lane; c4 < nchunks; c4 += 32) store_chunk(orow, c4, dim, 4, load_chunk(srow, c4, dim));
+}
+
+// Backward of the mean: one warp per target row; the row's gradient chunk is read once,
+// scaled by 1/cnt and pushed to every sampled neighbour's row with 128-bit reductions
+// (RED.ADD.F32x4 resolves at L2 -- no return value, no read-modify-write round trip).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+scatter_mean_kernel(const float* __restrict__ gout, int64_t ld_gout, int neigh_off, int dim,
+                    const int32_t* __restrict__ idx, const int32_t* __restrict__ cnt, int width,
+                    const int32_t* __restrict__ self_ids, int n_max, const int32_t* __restrict__ n_dev,
+                    float* __restrict__ gtable, int64_t ld_gtable, int in_align) {
+    const int n = gs_row_count(n_max, n_dev);
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int nchunks = (dim + 3) >> 2;
+    const int c = min(cnt[row], width);
+    const float inv = c > 0 ? 1.f / (float)c : 0.f;
+    const float* grow = gout + (int64_t)row * ld_gout;
+    const int32_t* irow = idx + (int64_t)row * width;
+    for (int c4 = lane; c4 < nchunks; c4 += 32) {
+        const int col = c4 * 4;
+        const bool full = col + 4 <= dim;
+        if (self_ids != nullptr) {
+            float4 g = load_chunk(grow, c4, dim);
+            float* dst = gtable + (int64_t)self_ids[row] * ld_gtable + col;
+            if (full) gs_red_add_v4(dst, g);
+            else { if (col < dim) atomicAdd(dst, g.x); if (col + 1 < dim) atomicAdd(dst + 1, g.y);
+                   if (col + 2 < dim) atomicAdd(dst + 2, g.z); }
+        }
+        float4 g;
+        const float* src = grow + neigh_off;
+        if (in_align == 4) g = load_chunk(src, c4, dim);
+        else {
+            g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col < dim) g.x = src[col];
+            if (col + 1 < dim) g.y = src[col + 1];
+            if (col + 2 < dim) g.z = src[col + 2];
+            if (col + 3 < dim) g.w = src[col + 3];
+        }
+        g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
+        for (int j = 0; j < c; ++j) {
+            float* dst = gtable + (int64_t)irow[j] * ld_gtable + col;
+            if (full) gs_red_add_v4(dst, g);
+            else { if (col < dim) atomicAdd(dst, g.x); if (col + 1 < dim) atomicAdd(dst + 1, g.y);
+                   if (col + 2 < dim) atomicAdd(dst + 2, g.z); }
+        }
+    }
+}
+
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float lr, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        p[i] = p[i] - lr * g[i];          // same two roundings as torch's add_(g, alpha=-lr)
+}
+
+}  // namespace
+
+extern "C" int gs_gather_mean_fwd(const float* table, int64_t ld_table, int32_t dim,
+                                  const int32_t* idx, const int32_t* cnt, int32_t width,
+                                  const int32_t* self_ids, int32_t n_max, const int32_t* n_dev,
+                                  float* out, int64_t ld_out, int32_t neigh_off, void* stream) {
+    if (!table || !idx || !cnt || !out || dim <= 0 || width <= 0 || n_max < 0 || neigh_off < 0) return GS_EINVAL;
+    if (!gs_aligned16(table) || !gs_aligned16(out) || (ld_table & 3) || (ld_out & 3)) return GS_EALIGN;
+    if (ld_table < dim || ld_out < neigh_off + dim) return GS_EINVAL;
+    if (n_max == 0) return GS_OK;
+    const int align = (neigh_off & 3) == 0 ? 4 : ((neigh_off & 1) == 0 ? 2 : 1);
+    const int nchunks = (dim + 3) / 4;
+    const dim3 grid((n_max + kWarpsPerBlock - 1) / kWarpsPerBlock), block(kWarpsPerBlock * 32);
+    cudaStream_t s = (cudaStream_t)stream;
+#define GS_GM(CH, NB) gather_mean_kernel<CH, NB><<<grid, block, 0, s>>>(table, ld_table, dim, idx, cnt, width, \
+        self_ids, n_max, n_dev, out, ld_out, neigh_off, align)
+    if (nchunks <= 32) GS_GM(1, 8);
+    else if (nchunks <= 64) GS_GM(2, 4);
+    else if (nchunks <= 96) GS_GM(3, 4);
+    else if (nchunks <= 128) GS_GM(4, 2);
+    else GS_GM(5, 2);
+#undef GS_GM
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+extern "C" int gs_gather_rows(const float* table, int64_t ld_table, int32_t dim, const int32_t* ids,
+                              int32_t n_max, const int32_t* n_dev, float* out, int64_t ld_out, void* stream) {
+    if (!table || !ids || !out || dim <= 0 || n_max < 0) return GS_EINVAL;
+    if (!gs_aligned16(table) || !gs_aligned16(out) || (ld_table & 3) || (ld_out & 3)) return GS_EALIGN;
+    if (ld_table < dim || ld_out < dim) return GS_EINVAL;
+    if (n_max == 0) return GS_OK;
+    gather_rows_kernel<<<(n_max + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        table, ld_table, dim, ids, n_max, n_dev, out, ld_out);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+extern "C" int gs_scatter_mean_bwd(const float* gout, int64_t ld_gout, int32_t neigh_off, int32_t dim,
+                                   const int32_t* idx, const int32_t* cnt, int32_t width,
+                                   const int32_t* self_ids, int32_t n_max, const int32_t* n_dev,
+                                   float* gtable, int64_t ld_gtable, void* stream) {
+    if (!gout || !idx || !cnt || !gtable || dim <= 0 || width <= 0 || n_max < 0 || neigh_off < 0) return GS_EINVAL;
+    if (!gs_aligned16(gout) || !gs_aligned16(gtable) || (ld_gout & 3) || (ld_gtable & 3)) return GS_EALIGN;
+    if (ld_gtable < dim || ld_gout < neigh_off + dim) return GS_EINVAL;
+    if (n_max == 0) return GS_OK;
+    const int align = (neigh_off & 3) == 0 ? 4 : 1;
+    scatter_mean_kernel<<<(n_max + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        gout, ld_gout, neigh_off, dim, idx, cnt, width, self_ids, n_max, n_dev, gtable, ld_gtable, align);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+extern "C" int gs_sgd_step(float* p, const float* g, float lr, int64_t n, void* stream) {
+    if (!p || !g || n < 0) return GS_EINVAL;
+    if (n == 0) return GS_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > GS_NUM_SMS * 8) blocks = GS_NUM_SMS * 8;
+    sgd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, lr, n);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}

@@ -1,0 +1,48 @@
+// Shared device/host helpers for libgsage_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/gsage.h"
+
+#define GS_NUM_SMS 148   // B200: 2 dies x 74 SMs
+
+#define GS_LAUNCH_CHECK()                                   \
+    do {                                                    \
+        cudaError_t e__ = cudaGetLastError();               \
+        if (e__ != cudaSuccess) return (int)e__;            \
+    } while (0)
+
+static inline bool gs_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__device__ __forceinline__ int gs_row_count(int n_max, const int32_t* n_dev) {
+    if (n_dev == nullptr) return n_max;
+    int n = __ldg(n_dev);
+    return n < n_max ? n : n_max;
+}
+
+// 128-bit read-only load that does not allocate in L1 (streaming feature rows).
+__device__ __forceinline__ float4 gs_ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void gs_red_add_v4(float* addr, float4 v) {
+    // sm_90+: vectorised fp32 reduction, one L2 atomic transaction per 16 bytes
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float gs_apply_act(float x, int act) {
+    if (act == GS_ACT_RELU) return x > 0.f ? x : 0.f;
+    if (act == GS_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
+    return x;
+}
+
+// derivative of the activation expressed through its OUTPUT y
+__device__ __forceinline__ float gs_act_grad(float y, int act) {
+    if (act == GS_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+    if (act == GS_ACT_SIGMOID) return y * (1.f - y);
+    return 1.f;
+}

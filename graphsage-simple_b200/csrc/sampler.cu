@@ -1,0 +1,269 @@
+// K1: CSR-resident counter-based neighbour sampler + frontier dedup.
+// Replaces graphsage/aggregators.py:42-56 and the adjacency lookup at encoders.py:47 of
+// the reference.  Specification restated on the CPU in oracle/sampler_port.py.
+#include "gs_common.cuh"
+
+namespace {
+
+constexpr int kMaxK = 64;          // largest sampled fan-out (Floyd set lives in registers/local)
+
+struct Philox {
+    uint32_t c[4];
+};
+
+__device__ __forceinline__ Philox philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    Philox p; p.c[0] = c0; p.c[1] = c1; p.c[2] = c2; p.c[3] = c3;
+    return p;
+}
+
+// One thread per frontier row.  Work per row is O(k^2) integer ops and k random 4-byte CSR
+// reads -- three orders of magnitude below the feature gather it feeds, so the simple
+// mapping is the right one; the grid is sized from n_max and trimmed by *n_dev.
+__global__ void __launch_bounds__(128)
+sample_csr_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                  const int32_t* __restrict__ nodes, int n_max, const int32_t* __restrict__ n_dev,
+                  int k, int width, int add_self, uint32_t seed_lo, uint32_t seed_hi,
+                  int64_t step_imm, const int64_t* __restrict__ step_dev,
+                  uint32_t tag_head, uint32_t tag_tail, int n_head,
+                  int32_t* __restrict__ idx, int32_t* __restrict__ cnt) {
+    const int n = gs_row_count(n_max, n_dev);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_max) return;
+    int32_t* out = idx + (int64_t)i * width;
+    if (i >= n) {                      // keep unused rows well defined for downstream kernels
+        for (int j = 0; j < width; ++j) out[j] = -1;
+        cnt[i] = 0;
+        return;
+    }
+    const int32_t v = nodes[i];
+    const int64_t base = rowptr[v];
+    const int deg = (int)(rowptr[v + 1] - base);
+    const uint32_t step = (uint32_t)(step_dev ? *step_dev : step_imm);
+    const uint32_t tag = i < n_head ? tag_head : tag_tail;
+    int c = 0;
+    bool has_self = false;
+    if (k < 0 || deg <= k) {
+        const int take = deg < width ? deg : width;
+        for (int j = 0; j < take; ++j) {
+            int32_t u = col[base + j];
+            has_self |= (u == v);
+            out[j] = u;
+        }
+        c = take;
+    } else {
+        int32_t pos[kMaxK];
+        Philox rnd;
+        for (int m = 0; m < k; ++m) {
+            if ((m & 3) == 0) rnd = philox4x32_10((uint32_t)v, (uint32_t)(m >> 2), step, tag, seed_lo, seed_hi);
+            const int j = deg - k + m;
+            const uint32_t r = rnd.c[m & 3];
+            int t = (int)(((uint64_t)r * (uint64_t)(j + 1)) >> 32);
+            bool dup = false;
+            for (int q = 0; q < m; ++q) dup |= (pos[q] == t);
+            if (dup) t = j;
+            // insertion keeps pos[] ascending
+            int q = m;
+            while (q > 0 && pos[q - 1] > t) { pos[q] = pos[q - 1]; --q; }
+            pos[q] = t;
+        }
+        for (int m = 0; m < k; ++m) {
+            int32_t u = col[base + pos[m]];
+            has_self |= (u == v);
+            out[m] = u;
+        }
+        c = k;
+    }
+    if (add_self && !has_self && c < width) out[c++] = v;
+    for (int j = c; j < width; ++j) out[j] = -1;
+    cnt[i] = c;
+}
+
+// ---- dedup: mark -> count(+scan of block sums by the last block) -> compact -> remap ----
+constexpr int kChunk = 2048;       // node ids per block in the count/compact passes
+constexpr int kScanThreads = 256;
+
+__global__ void dedup_mark_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ cnt,
+                                  int n_max, const int32_t* __restrict__ n_dev, int width,
+                                  int32_t* __restrict__ slot_of) {
+    const int n = gs_row_count(n_max, n_dev);
+    const int64_t total = (int64_t)n * width;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / width), j = (int)(e - (int64_t)i * width);
+        if (j < cnt[i]) slot_of[idx[e]] = 0;       // idempotent plain store: "present"
+    }
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total_out) {
+    // kScanThreads-wide exclusive scan (warp shuffles + one smem hop)
+    __shared__ int warp_sums[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const int before = w ? warp_sums[w - 1] : 0;
+    if (total_out) *total_out = warp_sums[kScanThreads / 32 - 1];
+    __syncthreads();
+    return before + inc - v;
+}
+
+// block_counts layout: [0..nb) per-block counts -> exclusive offsets, [nb] ticket counter
+__global__ void __launch_bounds__(kScanThreads)
+dedup_count_kernel(const int32_t* __restrict__ slot_of, int num_nodes, int nb,
+                   int32_t* __restrict__ block_counts, int slot_base, int32_t* __restrict__ n_total_dev) {
+    __shared__ int s_last;
+    const int lo = blockIdx.x * kChunk;
+    int mine = 0;
+    for (int t = threadIdx.x; t < kChunk; t += kScanThreads) {
+        const int id = lo + t;
+        mine += (id < num_nodes && slot_of[id] == 0) ? 1 : 0;
+    }
+    int total;
+    block_exclusive_scan(mine, &total);
+    if (threadIdx.x == 0) {
+        block_counts[blockIdx.x] = total;
+        __threadfence();
+        const int ticket = atomicAdd(&block_counts[nb], 1);
+        s_last = (ticket == nb - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last block: exclusive scan over the nb block sums (nb is small: num_nodes / 2048)
+    int carry = 0;
+    for (int b0 = 0; b0 < nb; b0 += kScanThreads) {
+        const int b = b0 + threadIdx.x;
+        const int v = b < nb ? ((volatile int32_t*)block_counts)[b] : 0;
+        int tot;
+        const int ex = block_exclusive_scan(v, &tot);
+        if (b < nb) block_counts[b] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        *n_total_dev = slot_base + carry;
+        block_counts[nb] = 0;                       // re-arm the ticket for the next call
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+dedup_compact_kernel(int32_t* __restrict__ slot_of, int num_nodes,
+                     const int32_t* __restrict__ block_counts, int slot_base,
+                     int32_t* __restrict__ uniq) {
+    const int lo = blockIdx.x * kChunk;
+    const int per = kChunk / kScanThreads;          // consecutive ids per thread keeps order
+    const int first = lo + threadIdx.x * per;
+    int flags = 0, mine = 0;
+#pragma unroll
+    for (int t = 0; t < per; ++t) {
+        const int id = first + t;
+        const int f = (id < num_nodes && slot_of[id] == 0) ? 1 : 0;
+        flags |= f << t;
+        mine += f;
+    }
+    int rank = block_counts[blockIdx.x] + block_exclusive_scan(mine, nullptr);
+#pragma unroll
+    for (int t = 0; t < per; ++t) {
+        if (flags >> t & 1) {
+            const int id = first + t;
+            uniq[rank] = id;
+            slot_of[id] = slot_base + rank;
+            ++rank;
+        }
+    }
+}
+
+__global__ void dedup_remap_kernel(int32_t* __restrict__ idx, const int32_t* __restrict__ cnt,
+                                   int n_max, const int32_t* __restrict__ n_dev, int width,
+                                   const int32_t* __restrict__ slot_of) {
+    const int n = gs_row_count(n_max, n_dev);
+    const int64_t total = (int64_t)n * width;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / width), j = (int)(e - (int64_t)i * width);
+        if (j < cnt[i]) idx[e] = slot_of[idx[e]];
+    }
+}
+
+__global__ void advance_step_kernel(int64_t* step) { *step += 1; }
+
+}  // namespace
+
+extern "C" int gs_sample_csr(const int64_t* rowptr, const int32_t* col, int32_t num_nodes,
+                             const int32_t* nodes, int32_t n_max, const int32_t* n_dev,
+                             int32_t k, int32_t width, int32_t add_self,
+                             uint64_t seed, int64_t step, const int64_t* step_dev,
+                             uint32_t tag_head, uint32_t tag_tail, int32_t n_head,
+                             int32_t* idx, int32_t* cnt, void* stream) {
+    (void)num_nodes;
+    if (!rowptr || !col || !nodes || !idx || !cnt || n_max < 0 || width <= 0) return GS_EINVAL;
+    if (k > kMaxK) return GS_ENOSUP;
+    if (k >= 0 && width < k + (add_self ? 1 : 0)) return GS_EINVAL;
+    if (n_max == 0) return GS_OK;
+    const int threads = 128;
+    sample_csr_kernel<<<(n_max + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+        rowptr, col, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed, (uint32_t)(seed >> 32),
+        step, step_dev, tag_head, tag_tail, n_head, idx, cnt);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+extern "C" int32_t gs_dedup_scratch_ints(int32_t num_nodes) {
+    return (num_nodes + kChunk - 1) / kChunk + 1;
+}
+
+extern "C" int gs_dedup_remap(int32_t* idx, const int32_t* cnt, int32_t n_max, const int32_t* n_dev,
+                              int32_t width, int32_t num_nodes, int32_t* slot_of, int32_t* block_counts,
+                              int32_t slot_base, int32_t* uniq, int32_t* n_total_dev, void* stream) {
+    if (!idx || !cnt || !slot_of || !block_counts || !uniq || !n_total_dev || num_nodes <= 0 || width <= 0 ||
+        n_max < 0)
+        return GS_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(slot_of, 0xFF, (size_t)num_nodes * sizeof(int32_t), s);
+    if (e != cudaSuccess) return (int)e;
+    const int nb = (num_nodes + kChunk - 1) / kChunk;
+    const int64_t entries = (int64_t)n_max * width;
+    int eb = (int)((entries + 255) / 256);
+    if (eb > GS_NUM_SMS * 8) eb = GS_NUM_SMS * 8;
+    if (eb < 1) eb = 1;
+    dedup_mark_kernel<<<eb, 256, 0, s>>>(idx, cnt, n_max, n_dev, width, slot_of);
+    GS_LAUNCH_CHECK();
+    dedup_count_kernel<<<nb, kScanThreads, 0, s>>>(slot_of, num_nodes, nb, block_counts, slot_base, n_total_dev);
+    GS_LAUNCH_CHECK();
+    dedup_compact_kernel<<<nb, kScanThreads, 0, s>>>(slot_of, num_nodes, block_counts, slot_base, uniq);
+    GS_LAUNCH_CHECK();
+    dedup_remap_kernel<<<eb, 256, 0, s>>>(idx, cnt, n_max, n_dev, width, slot_of);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+extern "C" int gs_advance_step(int64_t* step_dev, void* stream) {
+    if (!step_dev) return GS_EINVAL;
+    advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}

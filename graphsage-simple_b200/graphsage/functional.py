@@ -1,0 +1,71 @@
+"""autograd.Function wrappers that make the CUDA kernels participate in ``loss.backward()``
+the way the reference's ATen ops do (graphsage/model.py:249)."""
+import torch
+
+from . import ops
+
+
+class GatherMean(torch.autograd.Function):
+    """to_feats = mask.mm(embed_matrix) of aggregators.py:54-74 without the mask:
+    out[i] = mean_j table[idx[i, j]].  Backward is the scatter-add mask^T . g."""
+
+    @staticmethod
+    def forward(ctx, table, idx, cnt):
+        t = ops.aligned_rows(table)
+        n, dim = idx.shape[0], table.shape[1]
+        out = ops.empty_rows(n, dim, table.device)
+        ops.gather_mean_fwd(t, dim, idx, cnt, out, neigh_off=0)
+        ctx.save_for_backward(idx, cnt)
+        ctx.rows, ctx.dim = table.shape[0], dim
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        idx, cnt = ctx.saved_tensors
+        gtable = None
+        if ctx.needs_input_grad[0]:
+            gtable = ops.empty_rows(ctx.rows, ctx.dim, gout.device, zero=True)
+            ops.scatter_mean_bwd(ops.aligned_rows(gout), ctx.dim, idx, cnt, gtable, neigh_off=0)
+        return gtable, None, None
+
+
+class EncoderGemm(torch.autograd.Function):
+    """h[n, d_out] = act(x . w^T): ``F.relu(self.weight.mm(combined.t()))`` of encoders.py:58-61
+    in row-major form (the module returns the transposed view)."""
+
+    @staticmethod
+    def forward(ctx, x, w, act):
+        xa, wa = ops.aligned_rows(x), ops.aligned_rows(w)
+        h = ops.empty_rows(x.shape[0], w.shape[0], x.device)
+        ops.encoder_fwd(xa, wa, act, h)
+        ctx.save_for_backward(xa, wa, h)
+        ctx.act = act
+        return h
+
+    @staticmethod
+    def backward(ctx, gh):
+        xa, wa, h = ctx.saved_tensors
+        gw = ops.empty_rows(wa.shape[0], wa.shape[1], gh.device)
+        gx = ops.empty_rows(xa.shape[0], xa.shape[1], gh.device) if ctx.needs_input_grad[0] else None
+        ops.encoder_bwd(xa, wa, h, ops.aligned_rows(gh), ctx.act, gw, gx)
+        return gx, gw, None
+
+
+class SoftmaxXent(torch.autograd.Function):
+    """loss = CrossEntropyLoss()(h . wc^T, labels) (model.py:57, 64-69); the backward
+    quantities are produced by the same launch and rescaled by the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, h, wc, labels):
+        ha, wa = ops.aligned_rows(h), ops.aligned_rows(wc)
+        loss = torch.empty(1, device=h.device, dtype=torch.float32)
+        gh = ops.empty_rows(h.shape[0], h.shape[1], h.device)
+        gwc = ops.empty_rows(wc.shape[0], wc.shape[1], h.device)
+        ops.classifier_xent(ha, wa, labels, 1.0, None, loss, gh, gwc)
+        ctx.save_for_backward(gh, gwc)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        gh, gwc = ctx.saved_tensors
+        return gh * g, gwc * g, None

@@ -1,0 +1,180 @@
+"""Tensor-level wrappers over the C ABI (include/gsage.h).  Each function takes CUDA tensors,
+passes raw device pointers + sizes + the current stream to libgsage_sm100.so and raises on a
+non-zero return code.  Nothing here computes on the host."""
+import torch
+
+from . import _native as N
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+
+TAG_AGG2 = 2          # layer-2 aggregator over the targets        (RNG draw #2)
+TAG_AGG1_HOP = 1      # layer-1 aggregator over the hop-1 uniques  (RNG draw #1)
+TAG_AGG1_SELF = 3     # layer-1 aggregator over the batch nodes    (RNG draw #3)
+
+
+def round4(x):
+    return (int(x) + 3) // 4 * 4
+
+
+def empty_rows(n, d, device, dtype=torch.float32, zero=False):
+    """[n, d] fp32 view of a buffer whose leading dimension is a multiple of 4 floats."""
+    ld = round4(d)
+    buf = (torch.zeros if zero else torch.empty)((max(int(n), 1), ld), device=device, dtype=dtype)
+    return buf[:n, :d]
+
+
+def aligned_rows(x):
+    """Return x itself if it is a row-major fp32 CUDA matrix usable by the kernels (unit inner
+    stride, ld % 4 == 0, 16-B aligned base) else a padded copy."""
+    N.require_cuda(x)
+    if (x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 4 == 0
+            and x.stride(0) >= x.shape[1] and x.data_ptr() % 16 == 0):
+        return x
+    out = empty_rows(x.shape[0], x.shape[1], x.device)
+    out.copy_(x)
+    return out
+
+
+def as_ids(nodes, device):
+    """list / ndarray / LongTensor of node ids -> int32 CUDA tensor."""
+    if isinstance(nodes, torch.Tensor):
+        return nodes.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
+    import numpy as np
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(nodes, dtype=np.int32))).to(device, non_blocking=True)
+
+
+def sample_csr(rowptr, col, num_nodes, nodes, k, add_self=False, seed=0, step=0, tag_head=0,
+               tag_tail=None, n_head=None, n_dev=None, step_dev=None, width=None, idx=None, cnt=None):
+    """K1 -- see gs_sample_csr.  k=None means take-all (reference num_sample=None)."""
+    lib = N.load()
+    N.require_cuda(rowptr, col, nodes)
+    n_max = nodes.shape[0]
+    kk = -1 if k is None else int(k)
+    if width is None:
+        if kk < 0:
+            raise ValueError("width must be given for take-all sampling")
+        width = kk + (1 if add_self else 0)
+    width = max(int(width), 1)
+    if idx is None:
+        idx = torch.empty((max(n_max, 1), width), device=nodes.device, dtype=torch.int32)[:n_max]
+    if cnt is None:
+        cnt = torch.empty((max(n_max, 1),), device=nodes.device, dtype=torch.int32)[:n_max]
+    if tag_tail is None:
+        tag_tail = tag_head
+    if n_head is None:
+        n_head = n_max
+    N.check(lib.gs_sample_csr(N.ptr(rowptr), N.ptr(col), int(num_nodes), N.ptr(nodes), n_max, N.ptr(n_dev),
+                              kk, width, int(bool(add_self)), int(seed) & (2 ** 64 - 1), int(step), N.ptr(step_dev),
+                              int(tag_head), int(tag_tail), int(n_head), N.ptr(idx), N.ptr(cnt), N.stream()),
+            "gs_sample_csr")
+    return idx, cnt
+
+
+class DedupScratch:
+    """Reusable scratch for gs_dedup_remap over a graph with num_nodes ids."""
+
+    def __init__(self, num_nodes, device):
+        lib = N.load()
+        self.num_nodes = int(num_nodes)
+        self.slot_of = torch.empty(self.num_nodes, device=device, dtype=torch.int32)
+        self.block_counts = torch.zeros(lib.gs_dedup_scratch_ints(self.num_nodes), device=device, dtype=torch.int32)
+
+
+def dedup_remap(idx, cnt, scratch, slot_base=0, n_dev=None, uniq=None, n_total=None):
+    """Frontier dedup -- see gs_dedup_remap.  Rewrites idx in place; returns (uniq, n_total_dev)."""
+    lib = N.load()
+    N.require_cuda(idx, cnt)
+    n_max, width = idx.shape
+    if uniq is None:
+        uniq = torch.empty(max(min(n_max * width, scratch.num_nodes), 1), device=idx.device, dtype=torch.int32)
+    if n_total is None:
+        n_total = torch.zeros(1, device=idx.device, dtype=torch.int32)
+    N.check(lib.gs_dedup_remap(N.ptr(idx), N.ptr(cnt), n_max, N.ptr(n_dev), width, scratch.num_nodes,
+                               N.ptr(scratch.slot_of), N.ptr(scratch.block_counts), int(slot_base),
+                               N.ptr(uniq), N.ptr(n_total), N.stream()), "gs_dedup_remap")
+    return uniq, n_total
+
+
+def gather_mean_fwd(table, dim, idx, cnt, out, neigh_off=0, self_ids=None, n_dev=None):
+    lib = N.load()
+    N.require_cuda(table, idx, cnt, out)
+    n_max, width = idx.shape
+    N.check(lib.gs_gather_mean_fwd(N.ptr(table), table.stride(0), int(dim), N.ptr(idx), N.ptr(cnt), width,
+                                   N.ptr(self_ids), n_max, N.ptr(n_dev), N.ptr(out), out.stride(0),
+                                   int(neigh_off), N.stream()), "gs_gather_mean_fwd")
+    return out
+
+
+def scatter_mean_bwd(gout, dim, idx, cnt, gtable, neigh_off=0, self_ids=None, n_dev=None):
+    lib = N.load()
+    N.require_cuda(gout, idx, cnt, gtable)
+    n_max, width = idx.shape
+    N.check(lib.gs_scatter_mean_bwd(N.ptr(gout), gout.stride(0), int(neigh_off), int(dim), N.ptr(idx), N.ptr(cnt),
+                                    width, N.ptr(self_ids), n_max, N.ptr(n_dev), N.ptr(gtable), gtable.stride(0),
+                                    N.stream()), "gs_scatter_mean_bwd")
+    return gtable
+
+
+def gather_rows(table, dim, ids, out, n_dev=None):
+    lib = N.load()
+    N.require_cuda(table, ids, out)
+    N.check(lib.gs_gather_rows(N.ptr(table), table.stride(0), int(dim), N.ptr(ids), ids.shape[0], N.ptr(n_dev),
+                               N.ptr(out), out.stride(0), N.stream()), "gs_gather_rows")
+    return out
+
+
+def encoder_fwd(x, w, act, h, n_dev=None):
+    lib = N.load()
+    N.require_cuda(x, w, h)
+    n_max, k_in = x.shape
+    d_out = w.shape[0]
+    N.check(lib.gs_encoder_fwd(N.ptr(x), x.stride(0), N.ptr(w), w.stride(0), k_in, d_out, int(act), n_max,
+                               N.ptr(n_dev), N.ptr(h), h.stride(0), N.stream()), "gs_encoder_fwd")
+    return h
+
+
+def encoder_bwd_ws_floats(n_max, k_in, d_out):
+    return int(N.load().gs_encoder_bwd_ws_floats(int(n_max), int(k_in), int(d_out)))
+
+
+def encoder_bwd(x, w, h, gh, act, gw, gx=None, dz=None, ws=None, n_dev=None):
+    lib = N.load()
+    N.require_cuda(x, w, h, gh, gw)
+    n_max, k_in = x.shape
+    d_out = w.shape[0]
+    if dz is None:
+        dz = torch.empty((max(n_max, 1), d_out), device=x.device, dtype=torch.float32)
+    if ws is None:
+        ws = torch.empty(max(encoder_bwd_ws_floats(n_max, k_in, d_out), 4), device=x.device, dtype=torch.float32)
+    N.check(lib.gs_encoder_bwd(N.ptr(x), x.stride(0), N.ptr(w), w.stride(0), N.ptr(h), h.stride(0),
+                               N.ptr(gh), gh.stride(0), k_in, d_out, int(act), n_max, N.ptr(n_dev),
+                               N.ptr(dz), N.ptr(gw), gw.stride(0), N.ptr(gx), gx.stride(0) if gx is not None else 0,
+                               N.ptr(ws), N.stream()), "gs_encoder_bwd")
+    return gw, gx
+
+
+def classifier_xent(h, wc, labels, grad_scale=1.0, logits=None, loss=None, gh=None, gwc=None, ws=None):
+    lib = N.load()
+    N.require_cuda(h, wc, labels)
+    n, d = h.shape
+    c = wc.shape[0]
+    if ws is None:
+        ws = torch.empty(n * c + n, device=h.device, dtype=torch.float32)
+    N.check(lib.gs_classifier_xent(N.ptr(h), h.stride(0), N.ptr(wc), wc.stride(0), N.ptr(labels), d, c, n,
+                                   float(grad_scale), N.ptr(logits), logits.stride(0) if logits is not None else 0,
+                                   N.ptr(loss), N.ptr(gh), gh.stride(0) if gh is not None else 0,
+                                   N.ptr(gwc), gwc.stride(0) if gwc is not None else 0, N.ptr(ws), N.stream()),
+            "gs_classifier_xent")
+    return loss
+
+
+def sgd_step(p, g, lr):
+    lib = N.load()
+    N.require_cuda(p, g)
+    assert p.is_contiguous() and g.is_contiguous() and p.numel() == g.numel()
+    N.check(lib.gs_sgd_step(N.ptr(p), N.ptr(g), float(lr), p.numel(), N.stream()), "gs_sgd_step")
+    return p
+
+
+def advance_step(step_dev):
+    N.check(N.load().gs_advance_step(N.ptr(step_dev), N.stream()), "gs_advance_step")

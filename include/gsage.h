@@ -1,0 +1,155 @@
+/*
+ * gsage.h -- C ABI of libgsage_sm100.so: the B200 (sm_100a) implementation of GraphSAGE's
+ * sample -> aggregate -> update minibatch hot path.
+ *
+ * Every entry point below replaces one piece of zjzijielu/graphsage-simple's Python hot
+ * path (file:line cited per function, paths relative to the reference checkout).  The
+ * reference has no FFI of its own (it is pure Python/PyTorch); the binding a maintainer
+ * would add is a ctypes stub, shown in INTEGRATION.md and shipped as
+ * graphsage-simple_b200/graphsage/_native.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*
+ *   - `stream` is a cudaStream_t passed as void*; nothing here allocates, frees,
+ *     synchronises or touches the default stream, so every call is CUDA-graph capturable
+ *   - return value: 0 = ok, < 0 = argument error (GS_E*), > 0 = cudaError_t of the launch
+ *   - row counts come as (n_max, n_dev): n_max sizes the grid and the buffers; if n_dev is
+ *     non-NULL the kernels read the actual count (<= n_max) from device memory, so that a
+ *     captured graph can process data-dependent frontier sizes without a host round trip
+ *   - node ids and tile entries are int32, CSR row pointers int64, features/weights fp32
+ *   - all fp32 matrices are row-major with a leading dimension `ld*` in floats; `ld % 4 == 0`
+ *     and 16-byte aligned bases are required (128-bit loads)
+ *   - a "tile" is the fixed-width sampled neighbourhood: idx[n, width] (unused slots -1)
+ *     plus cnt[n]
+ */
+#ifndef GSAGE_H_
+#define GSAGE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GS_API __attribute__((visibility("default")))
+#else
+#define GS_API
+#endif
+
+#define GS_OK        0
+#define GS_EINVAL   -1   /* bad size / null pointer                       */
+#define GS_EALIGN   -2   /* pointer or leading dimension not 16-B aligned */
+#define GS_ENOSUP   -3   /* shape outside what the kernel supports        */
+
+#define GS_ACT_NONE    0
+#define GS_ACT_RELU    1  /* encoders.py:61 */
+#define GS_ACT_SIGMOID 2  /* encoders.py:59 (initializer in node_degree/shared/pagerank) */
+
+GS_API int gs_abi_version(void);
+GS_API const char* gs_strerror(int code);
+
+/* ---- K1: neighbour sampling ------------------------------------------------------------
+ * Replaces `random.sample(to_neigh, num_sample)` over adj_lists sets,
+ * graphsage/aggregators.py:42-48, the adjacency lookup graphsage/encoders.py:47 and the
+ * (intended) self-loop union aggregators.py:50-51.
+ * For row i (node v = nodes[i]): all neighbours when k < 0 or deg <= k, else a uniform
+ * k-subset drawn with Floyd's algorithm from Philox4x32-10(counter = (v, m/4, step, tag),
+ * key = seed); positions sorted, so tile entries ascend.  Rows i < n_head use tag_head,
+ * the rest tag_tail (the reference's independent aggregator calls of one forward).
+ * If step_dev != NULL the step is read from device memory (graph replay), else `step`.
+ * The exact specification is restated on the CPU in oracle/sampler_port.py.            */
+GS_API int gs_sample_csr(const int64_t* rowptr, const int32_t* col, int32_t num_nodes,
+                  const int32_t* nodes, int32_t n_max, const int32_t* n_dev,
+                  int32_t k, int32_t width, int32_t add_self,
+                  uint64_t seed, int64_t step, const int64_t* step_dev,
+                  uint32_t tag_head, uint32_t tag_tail, int32_t n_head,
+                  int32_t* idx, int32_t* cnt, void* stream);
+
+/* ---- frontier dedup ---------------------------------------------------------------------
+ * Replaces `unique_nodes_list = list(set.union(*samp_neighs))` and the id->column dict,
+ * aggregators.py:52-56.  Distinct ids of the tile, ascending, are written to uniq[0..U);
+ * the tile is rewritten in place as positions slot_base + rank; *n_total_dev = slot_base + U.
+ * slot_of[num_nodes] and block_counts[gs_dedup_scratch_ints(num_nodes)] are scratch.     */
+GS_API int32_t gs_dedup_scratch_ints(int32_t num_nodes);
+GS_API int gs_dedup_remap(int32_t* idx, const int32_t* cnt, int32_t n_max, const int32_t* n_dev,
+                   int32_t width, int32_t num_nodes, int32_t* slot_of, int32_t* block_counts,
+                   int32_t slot_base, int32_t* uniq, int32_t* n_total_dev, void* stream);
+
+/* ---- K2: gather-mean forward ------------------------------------------------------------
+ * Replaces the dense mask build, row-normalisation, feature lookup and `mask.mm(embed)`,
+ * aggregators.py:54-65, 74, plus the self lookup + torch.cat of encoders.py:49-54.
+ *   out[i, neigh_off : neigh_off+dim] = (1/cnt[i]) * sum_j table[idx[i,j], 0:dim]
+ *   out[i, 0:dim]                     = table[self_ids[i], 0:dim]      (if self_ids != NULL)
+ * Rows with cnt == 0 produce zeros (the reference produces NaN from 0/0).               */
+GS_API int gs_gather_mean_fwd(const float* table, int64_t ld_table, int32_t dim,
+                       const int32_t* idx, const int32_t* cnt, int32_t width,
+                       const int32_t* self_ids, int32_t n_max, const int32_t* n_dev,
+                       float* out, int64_t ld_out, int32_t neigh_off, void* stream);
+
+/* ---- K4: scatter-add backward of the mean ------------------------------------------------
+ * Replaces autograd's MmBackward of `mask.mm(embed_matrix)` (mask^T . g) and the
+ * CatBackward split, reached from loss.backward() at graphsage/model.py:249.
+ *   gtable[idx[i,j], 0:dim] += gout[i, neigh_off : neigh_off+dim] / cnt[i]
+ *   gtable[self_ids[i], 0:dim] += gout[i, 0:dim]                      (if self_ids != NULL)
+ * Accumulates with vectorised fp32 atomics into a caller-zeroed gtable.                 */
+GS_API int gs_scatter_mean_bwd(const float* gout, int64_t ld_gout, int32_t neigh_off, int32_t dim,
+                        const int32_t* idx, const int32_t* cnt, int32_t width,
+                        const int32_t* self_ids, int32_t n_max, const int32_t* n_dev,
+                        float* gtable, int64_t ld_gtable, void* stream);
+
+/* ---- K3: encoder GEMM + activation --------------------------------------------------------
+ * Replaces `F.relu(self.weight.mm(combined.t()))` / sigmoid, encoders.py:58-61.
+ *   h[i, 0:d_out] = act( sum_k x[i,k] * w[o,k] ),  x = combined [n, k_in], w [d_out, k_in].
+ * Output is row-major [n, d_out]; the reference's [d_out, n] is its transposed view.    */
+GS_API int gs_encoder_fwd(const float* x, int64_t ld_x, const float* w, int64_t ld_w,
+                   int32_t k_in, int32_t d_out, int32_t act,
+                   int32_t n_max, const int32_t* n_dev,
+                   float* h, int64_t ld_h, void* stream);
+
+/* Backward of the above (autograd ThresholdBackward/SigmoidBackward + MmBackward):
+ *   dz = gh * act'(h)                      (written to dz [n_max, d_out], ld = d_out)
+ *   gw[d_out, k_in]  = dz^T . x            (overwritten; split-K partials in ws)
+ *   gx[n, k_in]      = dz . w              (only if gx != NULL)
+ * ws must hold gs_encoder_bwd_ws_floats(n_max, k_in, d_out) floats.                      */
+GS_API int64_t gs_encoder_bwd_ws_floats(int32_t n_max, int32_t k_in, int32_t d_out);
+GS_API int gs_encoder_bwd(const float* x, int64_t ld_x, const float* w, int64_t ld_w,
+                   const float* h, int64_t ld_h, const float* gh, int64_t ld_gh,
+                   int32_t k_in, int32_t d_out, int32_t act,
+                   int32_t n_max, const int32_t* n_dev,
+                   float* dz, float* gw, int64_t ld_gw, float* gx, int64_t ld_gx,
+                   float* ws, void* stream);
+
+/* ---- K5: classifier + softmax cross-entropy, forward and backward -------------------------
+ * Replaces `scores = self.weight.mm(embeds).t()` and nn.CrossEntropyLoss (mean reduction),
+ * graphsage/model.py:57, 62-69, and their autograd backward.
+ *   logits[i, c] = sum_d h[i,d] * wc[c,d]            (written if logits != NULL)
+ *   loss[0]      = mean_i ( logsumexp(logits[i]) - logits[i, labels[i]] )
+ *   gh[i, :]     = grad_scale/n * (softmax(logits[i]) - onehot) . wc      (if gh  != NULL)
+ *   gwc[c, :]    = grad_scale/n * sum_i (softmax - onehot)[i,c] * h[i,:]  (if gwc != NULL)
+ * ws must hold n * num_classes + n floats.                                                */
+GS_API int gs_classifier_xent(const float* h, int64_t ld_h, const float* wc, int64_t ld_wc,
+                       const int64_t* labels, int32_t d, int32_t num_classes, int32_t n,
+                       float grad_scale, float* logits, int64_t ld_logits, float* loss,
+                       float* gh, int64_t ld_gh, float* gwc, int64_t ld_gwc,
+                       float* ws, void* stream);
+
+/* ---- K6: SGD -----------------------------------------------------------------------------
+ * Replaces torch.optim.SGD(lr=0.7).step(), graphsage/model.py:237, 250: p -= lr * g.      */
+GS_API int gs_sgd_step(float* p, const float* g, float lr, int64_t n, void* stream);
+
+/* Row gather without the mean (feature lookup aggregators.py:63-65 as a bit-exact copy):
+ * out[i, 0:dim] = table[ids[i], 0:dim].                                                  */
+GS_API int gs_gather_rows(const float* table, int64_t ld_table, int32_t dim, const int32_t* ids,
+                   int32_t n_max, const int32_t* n_dev, float* out, int64_t ld_out,
+                   void* stream);
+
+/* Small device-side helpers used to keep a training step free of host round trips.       */
+GS_API int gs_advance_step(int64_t* step_dev, void* stream);                    /* ++*step_dev   */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSAGE_H_ */

@@ -1,0 +1,69 @@
+"""CPU-side checks: the C-ABI library loads without a GPU and exports every symbol that
+include/gsage.h declares; the ctypes table matches the header; host-side containers."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "gsage.h")).read()
+    return re.findall(r"GS_API\s+[\w\s\*]+?\b(gs_\w+)\s*\(", text)
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    import __graft_entry__ as entry
+    return entry.build()
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    names = header_symbols()
+    assert len(names) >= 14
+    lib = ctypes.CDLL(lib_path)
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.gs_abi_version.restype = ctypes.c_int
+    assert lib.gs_abi_version() == 1
+
+
+def test_ctypes_table_matches_header(lib_path):
+    from graphsage import _native
+    assert sorted(_native.SIGNATURES) == sorted(header_symbols())
+    text = open(os.path.join(ROOT, "include", "gsage.h")).read()
+    for name, (_, args) in _native.SIGNATURES.items():
+        m = re.search(r"GS_API[^;(]*\b%s\s*\(([^;]*?)\)\s*;" % name, text, re.S)
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(args), (name, len(params), len(args))
+    assert _native.load().gs_strerror(-2).decode().startswith("gsage:")
+
+
+def test_argument_errors_are_codes_not_crashes(lib_path):
+    from graphsage import _native
+    lib = _native.load()
+    assert lib.gs_sgd_step(None, None, 0.1, 10, None) == -1
+    assert lib.gs_gather_rows(None, 0, 4, None, 1, None, None, 0, None) == -1
+    assert lib.gs_encoder_bwd_ws_floats(1024, 256, 128) > 0
+    assert lib.gs_dedup_scratch_ints(233000) == 233000 // 2048 + 2
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "graphsage-simple_b200", "graphsage")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+
+
+def test_modules_refuse_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import torch.nn as nn
+    from graphsage.aggregators import MeanAggregator
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        MeanAggregator(nn.Embedding(4, 4))

@@ -1,0 +1,266 @@
+"""Kernel-level parity (through the C ABI) against the CPU oracle on seeded inputs.
+Integer/index work is bit-exact; fp32 work is checked norm-wise at 1e-5 (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sampler_port as SP
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5          # north_star: fp32 outputs within 1e-5 relative (norm-wise)
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def random_csr(rng, n, avg_deg, hub=0):
+    deg = rng.poisson(avg_deg, n).astype(np.int64)
+    deg[rng.integers(0, n, max(n // 50, 1))] = 0          # some isolated nodes
+    if hub:
+        deg[rng.integers(0, n, 3)] = hub
+    deg = np.minimum(deg, n)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    col = np.concatenate([np.sort(rng.choice(n, size=d, replace=False)) for d in deg] + [np.zeros(0, np.int64)])
+    return rowptr, col.astype(np.int32)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from graphsage import ops as o
+    return o
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("k,add_self", [(5, False), (10, False), (25, True), (1, False), (None, False), (None, True)])
+def test_sampler_bit_exact(ops, k, add_self):
+    rng = np.random.default_rng(3)
+    n = 3000
+    rowptr, col = random_csr(rng, n, 12, hub=200)
+    nodes = rng.integers(0, n, 1777).astype(np.int32)
+    tags = np.where(np.arange(nodes.size) < 700, 7, 9).astype(np.uint32)
+    width = None if k is not None else int(np.diff(rowptr).max()) + (1 if add_self else 0)
+    idx, cnt = ops.sample_csr(dev(rowptr), dev(col), n, dev(nodes), k, add_self=add_self, seed=0x1234567890ABCDEF,
+                              step=41, tag_head=7, tag_tail=9, n_head=700, width=width)
+    ridx, rcnt = SP.sample_csr(rowptr, col, nodes, -1 if k is None else k, 0x1234567890ABCDEF, 41, tags,
+                               add_self=add_self, width=width)
+    assert np.array_equal(cnt.cpu().numpy(), rcnt)
+    assert np.array_equal(idx.cpu().numpy(), ridx)
+
+
+def test_sampler_semantics_match_reference(ops):
+    """aggregators.py:42-48: all neighbours when deg < k (== k gives the same set), exactly k
+    distinct members of the adjacency otherwise; different steps/tags give different draws."""
+    rng = np.random.default_rng(5)
+    n, k = 2000, 10
+    rowptr, col = random_csr(rng, n, 14)
+    nodes = np.arange(n, dtype=np.int32)
+    idx, cnt = ops.sample_csr(dev(rowptr), dev(col), n, dev(nodes), k, seed=9, step=1, tag_head=1)
+    idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+    deg = np.diff(rowptr)
+    assert np.array_equal(cnt, np.minimum(deg, k))
+    for v in range(n):
+        row = idx[v, :cnt[v]]
+        adj = col[rowptr[v]:rowptr[v + 1]]
+        assert len(set(row.tolist())) == cnt[v] and np.isin(row, adj).all()
+        if deg[v] <= k:
+            assert np.array_equal(row, adj)
+        assert (idx[v, cnt[v]:] == -1).all()
+    idx2, _ = ops.sample_csr(dev(rowptr), dev(col), n, dev(nodes), k, seed=9, step=2, tag_head=1)
+    assert (idx2.cpu().numpy() != idx).any()
+
+
+def test_sampler_uniform_marginals(ops):
+    """chi-square on the inclusion counts of one 40-neighbour row over 4000 steps."""
+    deg, k, steps = 40, 10, 4000
+    rowptr = np.array([0, deg], dtype=np.int64)
+    col = np.arange(100, 100 + deg, dtype=np.int32)
+    counts = np.zeros(deg)
+    nodes = dev(np.zeros(1, dtype=np.int32))
+    rp, cl = dev(rowptr), dev(col)
+    for s in range(steps):
+        idx, _ = ops.sample_csr(rp, cl, 1, nodes, k, seed=77, step=s, tag_head=3)
+        counts[idx.cpu().numpy()[0] - 100] += 1
+    expect = steps * k / deg
+    chi2 = ((counts - expect) ** 2 / (expect * (1 - k / deg))).sum()
+    assert chi2 < 80.0, chi2            # 39 dof: P(chi2 > 80) ~ 1e-4
+
+
+@pytest.mark.parametrize("n_rows,width,num_nodes", [(1000, 25, 5000), (37, 3, 50), (4096, 10, 233000), (1, 1, 3)])
+def test_dedup_bit_exact(ops, n_rows, width, num_nodes):
+    rng = np.random.default_rng(8)
+    cnt = rng.integers(0, width + 1, n_rows).astype(np.int32)
+    idx = rng.integers(0, num_nodes, (n_rows, width)).astype(np.int32)
+    idx[np.arange(width)[None, :] >= cnt[:, None]] = -1
+    scratch = ops.DedupScratch(num_nodes, "cuda")
+    for rep in range(2):                                   # the scratch re-arms itself
+        d_idx = dev(idx)
+        uniq, total = ops.dedup_remap(d_idx, dev(cnt), scratch, slot_base=17)
+        ru, ridx = SP.dedup_remap(idx, cnt, slot_base=17)
+        u = int(total.item()) - 17
+        assert u == ru.size
+        assert np.array_equal(uniq.cpu().numpy()[:u], ru)
+        assert np.array_equal(d_idx.cpu().numpy(), ridx)
+
+
+def test_dedup_device_row_count(ops):
+    rng = np.random.default_rng(9)
+    idx = rng.integers(0, 100, (64, 4)).astype(np.int32)
+    cnt = np.full(64, 4, dtype=np.int32)
+    d_idx = dev(idx)
+    n_dev = torch.tensor([20], dtype=torch.int32, device="cuda")
+    uniq, total = ops.dedup_remap(d_idx, dev(cnt), ops.DedupScratch(100, "cuda"), n_dev=n_dev)
+    ru, ridx = SP.dedup_remap(idx[:20], cnt[:20])
+    assert int(total.item()) == ru.size
+    assert np.array_equal(d_idx.cpu().numpy()[:20], ridx)
+    assert np.array_equal(d_idx.cpu().numpy()[20:], idx[20:])      # untouched beyond *n_dev
+
+
+def make_tile(rng, n, width, rows, empty_rows=True):
+    cnt = rng.integers(1, width + 1, n).astype(np.int32)
+    if empty_rows:
+        cnt[rng.integers(0, n, max(n // 20, 1))] = 0
+    idx = rng.integers(0, rows, (n, width)).astype(np.int32)
+    idx[np.arange(width)[None, :] >= cnt[:, None]] = -1
+    return idx, cnt
+
+
+def ref_gather_mean(table, idx, cnt):
+    out = np.zeros((idx.shape[0], table.shape[1]), dtype=np.float64)
+    for i in range(idx.shape[0]):
+        if cnt[i]:
+            out[i] = table[idx[i, :cnt[i]]].astype(np.float64).sum(0) / cnt[i]
+    return out
+
+
+@pytest.mark.parametrize("dim,width,with_self", [(602, 10, True), (128, 25, True), (50, 5, False), (1433, 10, False),
+                                                 (3703, 5, True), (7, 40, False), (100, 15, True)])
+def test_gather_mean_forward(ops, dim, width, with_self):
+    rng = np.random.default_rng(dim)
+    rows, n = 5000, 777
+    table = rng.standard_normal((rows, dim)).astype(np.float32)
+    idx, cnt = make_tile(rng, n, width, rows)
+    self_ids = rng.integers(0, rows, n).astype(np.int32)
+    t = ops.aligned_rows(dev(table))
+    off = dim if with_self else 0
+    out = ops.empty_rows(n, off + dim, "cuda", zero=True)
+    ops.gather_mean_fwd(t, dim, dev(idx), dev(cnt), out, neigh_off=off, self_ids=dev(self_ids) if with_self else None)
+    got = out.cpu().numpy()
+    ref = ref_gather_mean(table, idx, cnt)
+    assert relerr(got[:, off:], ref) < REL
+    if with_self:
+        assert np.array_equal(got[:, :dim], table[self_ids])       # gathered rows: bit-exact copy
+
+
+def test_gather_rows_bit_exact(ops):
+    rng = np.random.default_rng(12)
+    table = rng.standard_normal((1000, 602)).astype(np.float32)
+    ids = rng.integers(0, 1000, 333).astype(np.int32)
+    out = ops.empty_rows(333, 602, "cuda")
+    ops.gather_rows(ops.aligned_rows(dev(table)), 602, dev(ids), out)
+    assert np.array_equal(out.cpu().numpy(), table[ids])
+
+
+@pytest.mark.parametrize("dim,width,with_self,off", [(128, 25, True, 128), (50, 5, False, 0), (602, 10, True, 602), (30, 7, True, 30)])
+def test_scatter_mean_backward(ops, dim, width, with_self, off):
+    rng = np.random.default_rng(dim + 1)
+    rows, n = 900, 1500               # many duplicates -> contention on the atomics
+    idx, cnt = make_tile(rng, n, width, rows)
+    self_ids = rng.integers(0, rows, n).astype(np.int32)
+    gout = rng.standard_normal((n, off + dim)).astype(np.float32)
+    gtable = ops.empty_rows(rows, dim, "cuda", zero=True)
+    ops.scatter_mean_bwd(ops.aligned_rows(dev(gout)), dim, dev(idx), dev(cnt), gtable, neigh_off=off,
+                         self_ids=dev(self_ids) if with_self else None)
+    ref = np.zeros((rows, dim), dtype=np.float64)
+    for i in range(n):
+        if cnt[i]:
+            np.add.at(ref, idx[i, :cnt[i]], gout[i, off:off + dim].astype(np.float64) / cnt[i])
+        if with_self:
+            ref[self_ids[i]] += gout[i, :dim]
+    assert relerr(gtable.cpu().numpy(), ref) < REL
+
+
+@pytest.mark.parametrize("n,k_in,d_out,act", [(1000, 1204, 128, 1), (333, 256, 128, 1), (77, 1433, 50, 2),
+                                              (5000, 100, 128, 1), (64, 36, 12, 0), (1, 8, 4, 1), (2049, 602, 128, 2)])
+def test_encoder_forward_backward(ops, n, k_in, d_out, act):
+    rng = np.random.default_rng(n + k_in)
+    x = rng.standard_normal((n, k_in)).astype(np.float32)
+    w = (rng.standard_normal((d_out, k_in)) / np.sqrt(k_in)).astype(np.float32)
+    gh = rng.standard_normal((n, d_out)).astype(np.float32)
+    xd, wd, ghd = ops.aligned_rows(dev(x)), ops.aligned_rows(dev(w)), ops.aligned_rows(dev(gh))
+    h = ops.empty_rows(n, d_out, "cuda")
+    ops.encoder_fwd(xd, wd, act, h)
+    tx = torch.from_numpy(x).double().requires_grad_(True)
+    tw = torch.from_numpy(w).double().requires_grad_(True)
+    pre = tx @ tw.t()
+    th = {0: pre, 1: torch.relu(pre), 2: torch.sigmoid(pre)}[act]
+    assert relerr(h.cpu().numpy(), th.detach().numpy()) < REL
+    th.backward(torch.from_numpy(gh).double())
+    gw = ops.empty_rows(d_out, k_in, "cuda")
+    gx = ops.empty_rows(n, k_in, "cuda")
+    ops.encoder_bwd(xd, wd, h, ghd, act, gw, gx)
+    assert relerr(gw.cpu().numpy(), tw.grad.numpy()) < REL
+    assert relerr(gx.cpu().numpy(), tx.grad.numpy()) < REL
+
+
+def test_encoder_device_row_count(ops):
+    rng = np.random.default_rng(4)
+    n_max, n, k_in, d_out = 600, 417, 64, 32
+    x = rng.standard_normal((n_max, k_in)).astype(np.float32)
+    w = rng.standard_normal((d_out, k_in)).astype(np.float32)
+    gh = rng.standard_normal((n_max, d_out)).astype(np.float32)
+    n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
+    xd, wd = dev(x), dev(w)
+    h = torch.full((n_max, d_out), 7.0, device="cuda")
+    ops.encoder_fwd(xd, wd, 1, h, n_dev=n_dev)
+    ref = np.maximum(x[:n].astype(np.float64) @ w.T.astype(np.float64), 0)
+    assert relerr(h.cpu().numpy()[:n], ref) < REL
+    assert (h.cpu().numpy()[n:] == 7.0).all()
+    gw = ops.empty_rows(d_out, k_in, "cuda")
+    ops.encoder_bwd(xd, wd, h, dev(gh), 1, gw, None, n_dev=n_dev)
+    dz = gh[:n].astype(np.float64) * (ref > 0)
+    assert relerr(gw.cpu().numpy(), dz.T @ x[:n].astype(np.float64)) < REL
+
+
+@pytest.mark.parametrize("n,d,c", [(1024, 128, 41), (48, 12, 6), (5, 128, 3), (300, 128, 47), (100, 64, 100)])
+def test_classifier_xent(ops, n, d, c):
+    rng = np.random.default_rng(n + c)
+    h = rng.standard_normal((n, d)).astype(np.float32)
+    wc = (rng.standard_normal((c, d)) * 0.3).astype(np.float32)
+    y = rng.integers(0, c, n).astype(np.int64)
+    hd, wd = ops.aligned_rows(dev(h)), ops.aligned_rows(dev(wc))
+    logits = ops.empty_rows(n, c, "cuda")
+    loss = torch.zeros(1, device="cuda")
+    gh = ops.empty_rows(n, d, "cuda")
+    gwc = ops.empty_rows(c, d, "cuda")
+    ops.classifier_xent(hd, wd, dev(y), 1.0, logits, loss, gh, gwc)
+    th = torch.from_numpy(h).double().requires_grad_(True)
+    tw = torch.from_numpy(wc).double().requires_grad_(True)
+    tl = torch.nn.functional.cross_entropy(th @ tw.t(), torch.from_numpy(y))
+    tl.backward()
+    assert relerr(logits.cpu().numpy(), (th @ tw.t()).detach().numpy()) < REL
+    assert abs(float(loss.item()) - float(tl)) / abs(float(tl)) < REL
+    assert relerr(gh.cpu().numpy(), th.grad.numpy()) < REL
+    assert relerr(gwc.cpu().numpy(), tw.grad.numpy()) < REL
+
+
+def test_sgd_step_bit_exact(ops):
+    rng = np.random.default_rng(1)
+    p = rng.standard_normal(100003).astype(np.float32)
+    g = rng.standard_normal(100003).astype(np.float32)
+    pd = dev(p)
+    ops.sgd_step(pd, dev(g), 0.7)
+    ref = torch.from_numpy(p).add_(torch.from_numpy(g), alpha=-0.7).numpy()      # model.py:237, 250
+    assert np.array_equal(pd.cpu().numpy(), ref)
+
+
+def test_cpu_tensors_are_rejected(ops):
+    with pytest.raises(RuntimeError):
+        ops.gather_rows(torch.zeros(4, 4), 4, torch.zeros(2, dtype=torch.int32), torch.zeros(2, 4))
