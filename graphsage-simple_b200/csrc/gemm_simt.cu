@@ -179,12 +179,13 @@ gemm_kernel(GemmArgs g) {
 
 // dz = gh * act'(h); rows >= n are written as zeros so later reductions over n_max are safe
 __global__ void act_grad_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restrict__ gh, int64_t ld_gh,
-                                int d, int act, int n_max, const int32_t* __restrict__ n_dev, float* __restrict__ dz) {
+                                int d, int act, int n_max, const int32_t* __restrict__ n_dev, float* __restrict__ dz,
+                                int ld_dz) {
     const int n = gs_row_count(n_max, n_dev);
     const int64_t total = (int64_t)n_max * d;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int i = (int)(e / d), j = (int)(e - (int64_t)i * d);
-        dz[e] = i < n ? gh[(int64_t)i * ld_gh + j] * gs_act_grad(h[(int64_t)i * ld_h + j], act) : 0.f;
+        dz[(int64_t)i * ld_dz + j] = i < n ? gh[(int64_t)i * ld_gh + j] * gs_act_grad(h[(int64_t)i * ld_h + j], act) : 0.f;
     }
 }
 
@@ -249,15 +250,16 @@ extern "C" int gs_encoder_bwd(const float* x, int64_t ld_x, const float* w, int6
                               float* ws, void* stream) {
     if (!x || !w || !h || !gh || !dz || !gw || !ws || k_in <= 0 || d_out <= 0 || n_max < 0) return GS_EINVAL;
     if (!gs_aligned16(x) || !gs_aligned16(w) || !gs_aligned16(dz) || !gs_aligned16(ws) || (ld_x & 3) || (ld_w & 3) ||
-        (d_out & 3) || (gx && (!gs_aligned16(gx) || (ld_gx & 3))))
+        (gx && (!gs_aligned16(gx) || (ld_gx & 3))))
         return GS_EALIGN;
+    const int ld_dz = (d_out + 3) & ~3;
     if (n_max == 0) return GS_OK;
     cudaStream_t s = (cudaStream_t)stream;
     {
         const int64_t total = (int64_t)n_max * d_out;
         int64_t blocks = (total + 255) / 256;
         if (blocks > GS_NUM_SMS * 8) blocks = GS_NUM_SMS * 8;
-        act_grad_kernel<<<(int)blocks, 256, 0, s>>>(h, ld_h, gh, ld_gh, d_out, act, n_max, n_dev, dz);
+        act_grad_kernel<<<(int)blocks, 256, 0, s>>>(h, ld_h, gh, ld_gh, d_out, act, n_max, n_dev, dz, ld_dz);
         GS_LAUNCH_CHECK();
     }
     // gw[d_out, k_in] = dz^T . x   (reduction over the n rows, split-K with ordered partials)
@@ -266,7 +268,7 @@ extern "C" int gs_encoder_bwd(const float* x, int64_t ld_x, const float* w, int6
     kper = ((kper + BK - 1) / BK) * BK;
     const bool direct = splits == 1 && (ld_gw & 3) == 0 && gs_aligned16(gw);
     const int64_t ld_ws = (k_in + 3) & ~3;          // keeps every partial row 16-B aligned
-    GemmArgs g{dz, d_out, x, ld_x, direct ? gw : ws, direct ? ld_gw : ld_ws, d_out, k_in, n_max, n_dev, 1,
+    GemmArgs g{dz, ld_dz, x, ld_x, direct ? gw : ws, direct ? ld_gw : ld_ws, d_out, k_in, n_max, n_dev, 1,
                GS_ACT_NONE, kper, (int64_t)d_out * ld_ws};
     int rc = launch_gemm<true, true>(g, splits, s);
     if (rc) return rc;
@@ -278,7 +280,7 @@ extern "C" int gs_encoder_bwd(const float* x, int64_t ld_x, const float* w, int6
         GS_LAUNCH_CHECK();
     }
     if (gx) {   // gx[n, k_in] = dz . w
-        GemmArgs gd{dz, d_out, w, ld_w, gx, ld_gx, n_max, k_in, d_out, n_dev, 0, GS_ACT_NONE, ((d_out + BK - 1) / BK) * BK, 0};
+        GemmArgs gd{dz, ld_dz, w, ld_w, gx, ld_gx, n_max, k_in, d_out, n_dev, 0, GS_ACT_NONE, ((d_out + BK - 1) / BK) * BK, 0};
         rc = launch_gemm<false, true>(gd, 1, s);
         if (rc) return rc;
     }

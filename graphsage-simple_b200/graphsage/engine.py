@@ -1,0 +1,272 @@
+"""Fused 2-layer train step: sample -> aggregate -> update with no host round trip.
+
+This is the unit the reference times at graphsage/model.py:245-252 (zero_grad, loss,
+backward, SGD step) for the wiring of model.py:214-227: a frozen feature table, layer-1
+Encoder, layer-2 Encoder reached through the closure ``lambda nodes: enc1(nodes).t()``, and
+the SupervisedGraphSage classifier.  Instead of recursing through Python closures and
+autograd, the engine lays the whole step out over statically allocated HBM buffers:
+
+  targets[B] --K1--> tile2[B,k2] --dedup--> frontier1 = [targets | distinct hop-1 ids]
+  frontier1[n1] --K1--> tile1[n1,k1] --K2--> comb1[n1, 2F] = [x_v | mean x_u] --K3--> h1[n1,d1]
+  tile2 (slots into h1) --K2--> comb2[B, 2d1] = [h1_t | mean h1_u] --K3--> h2[B,d2]
+  h2 --K5--> loss, dh2, dWc --K3'--> dW2, dcomb2 --K4--> dh1 --K3'--> dW1 --(NCCL)--> K6 SGD
+
+``n1`` (the number of layer-1 evaluations, B + |distinct hop-1 ids|) only exists in device
+memory; every kernel takes (n_max, n_dev), so the sequence is a fixed list of launches and is
+captured once per batch size into a CUDA graph.  All arithmetic is in the kernels of
+libgsage_sm100.so; torch supplies memory, streams, graphs and NCCL.
+"""
+import numpy as np
+import torch
+
+from . import ops, sampling
+
+_SIGMOID = ("node_degree", "shared", "pagerank")
+
+
+class TrainEngine:
+    def __init__(self, graph1, graph2, table, feat_dim, d1, d2, num_classes, k1, k2, max_batch,
+                 gcn=False, agg_gcn1=False, agg_gcn2=False, act1=ops.ACT_RELU, act2=ops.ACT_RELU,
+                 uid1=1, uid2=2, device=None, use_graphs=True):
+        self.dev = torch.device(device) if device is not None else table.device
+        self.g1, self.g2 = graph1, graph2
+        self.table = ops.aligned_rows(table)
+        self.F, self.d1, self.d2, self.C = int(feat_dim), int(d1), int(d2), int(num_classes)
+        self.k1, self.k2 = k1, k2
+        self.gcn, self.agg_gcn1, self.agg_gcn2 = bool(gcn), bool(agg_gcn1), bool(agg_gcn2)
+        self.act1, self.act2 = act1, act2
+        self.uid1, self.uid2 = uid1, uid2
+        self.use_graphs = use_graphs
+        self.B = int(max_batch)
+        dev = self.dev
+        B = self.B
+        self.w2_width = (k2 if k2 is not None else graph2.max_degree) + (1 if agg_gcn2 else 0)
+        self.w1_width = (k1 if k1 is not None else graph1.max_degree) + (1 if agg_gcn1 else 0)
+        self.w2_width, self.w1_width = max(self.w2_width, 1), max(self.w1_width, 1)
+        self.slot_base_of = (lambda b: 0) if self.gcn else (lambda b: b)
+        n1_max = min(B * self.w2_width, graph2.num_nodes) + (0 if self.gcn else B)
+        self.n1_max = n1_max
+        self.K1 = self.F if self.gcn else 2 * self.F
+        self.K2 = self.d1 if self.gcn else 2 * self.d1
+        i32 = dict(device=dev, dtype=torch.int32)
+        # per-step inputs: one pinned staging block [step | labels | targets] -> one H2D copy
+        self.stage_host = torch.empty(8 + 8 * B + 4 * B, dtype=torch.uint8).pin_memory()
+        self.stage_dev = torch.empty(8 + 8 * B + 4 * B, dtype=torch.uint8, device=dev)
+        self.step_dev = self.stage_dev[:8].view(torch.int64)
+        self.labels = self.stage_dev[8:8 + 8 * B].view(torch.int64)
+        self.targets = self.stage_dev[8 + 8 * B:].view(torch.int32)
+        self.loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+        # sampled structure
+        self.idx2 = torch.empty((B, self.w2_width), **i32)
+        self.cnt2 = torch.empty(B, **i32)
+        self.frontier1 = torch.zeros(n1_max, **i32)
+        self.n1_dev = torch.zeros(1, **i32)
+        self.idx1 = torch.empty((n1_max, self.w1_width), **i32)
+        self.cnt1 = torch.empty(n1_max, **i32)
+        self.self2 = torch.arange(B, **i32)
+        self.scratch = ops.DedupScratch(graph2.num_nodes, dev)
+        # activations (row-major, ld % 4 == 0)
+        self.comb1 = ops.empty_rows(n1_max, self.K1, dev, zero=True)
+        self.h1 = ops.empty_rows(n1_max, self.d1, dev, zero=True)
+        self.comb2 = ops.empty_rows(B, self.K2, dev, zero=True)
+        self.h2 = ops.empty_rows(B, self.d2, dev, zero=True)
+        self.logits = ops.empty_rows(B, self.C, dev, zero=True)
+        self.loss = torch.zeros(1, device=dev)
+        # gradients of activations
+        self.gh2 = ops.empty_rows(B, self.d2, dev, zero=True)
+        self.gcomb2 = ops.empty_rows(B, self.K2, dev, zero=True)
+        self.gh1 = ops.empty_rows(n1_max, self.d1, dev, zero=True)
+        self.dz2 = torch.empty((B, ops.round4(self.d2)), device=dev)
+        self.dz1 = torch.empty((n1_max, ops.round4(self.d1)), device=dev)
+        ws = max(ops.encoder_bwd_ws_floats(n1_max, self.K1, self.d1),
+                 ops.encoder_bwd_ws_floats(B, self.K2, self.d2), 4)
+        self.ws = torch.empty(ws, device=dev)
+        self.xent_ws = torch.empty(B * self.C + B, device=dev)
+        # parameters + gradients: one flat block each (padded rows), module params alias into it
+        shapes = [(self.d1, self.K1), (self.d2, self.K2), (self.C, self.d2)]
+        sizes = [r * ops.round4(c) for r, c in shapes]
+        self.flat_w = torch.zeros(sum(sizes), device=dev)
+        self.flat_g = torch.zeros(sum(sizes), device=dev)
+        views_w, views_g, off = [], [], 0
+        for (r, c), sz in zip(shapes, sizes):
+            views_w.append(self.flat_w[off:off + sz].view(r, ops.round4(c))[:, :c])
+            views_g.append(self.flat_g[off:off + sz].view(r, ops.round4(c))[:, :c])
+            off += sz
+        self.w1, self.w2, self.wc = views_w
+        self.gw1, self.gw2, self.gwc = views_g
+        self._graphs = {}
+        self._warm = set()
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ the launch sequence
+    def _forward_backward(self, b):
+        """Enqueue one fwd+bwd over the first ``b`` staged targets on the current stream."""
+        seed = sampling.get_seed()
+        base = self.slot_base_of(b)
+        targets, labels = self.targets[:b], self.labels[:b]
+        idx2, cnt2 = self.idx2[:b], self.cnt2[:b]
+        n = 0
+        # layer-2 tile over the targets (aggregators.py:42-48; RNG draw of agg2)
+        ops.sample_csr(self.g2.rowptr, self.g2.col, self.g2.num_nodes, targets, self.k2, add_self=self.agg_gcn2,
+                       seed=seed, step_dev=self.step_dev, tag_head=sampling.call_tag(self.uid2, 0),
+                       width=self.w2_width, idx=idx2, cnt=cnt2)
+        # frontier of layer 1: [targets (SAGE self pass) | distinct hop-1 ids] (aggregators.py:52-56)
+        if not self.gcn:
+            self.frontier1[:b].copy_(targets)
+        ops.dedup_remap(idx2, cnt2, self.scratch, slot_base=base, uniq=self.frontier1[base:], n_total=self.n1_dev)
+        n1_max = min(b * self.w2_width, self.g2.num_nodes) + base
+        fr = self.frontier1[:n1_max]
+        idx1, cnt1 = self.idx1[:n1_max], self.cnt1[:n1_max]
+        # layer-1 tiles: rows < b are the self pass over the batch nodes (independent draw,
+        # call index 1), the rest the hop-1 pass (call index 0)  -- SURVEY.md s3.2
+        ops.sample_csr(self.g1.rowptr, self.g1.col, self.g1.num_nodes, fr, self.k1, add_self=self.agg_gcn1,
+                       seed=seed, step_dev=self.step_dev, tag_head=sampling.call_tag(self.uid1, 1),
+                       tag_tail=sampling.call_tag(self.uid1, 0), n_head=base, n_dev=self.n1_dev,
+                       width=self.w1_width, idx=idx1, cnt=cnt1)
+        comb1, h1 = self.comb1[:n1_max], self.h1[:n1_max]
+        ops.gather_mean_fwd(self.table, self.F, idx1, cnt1, comb1, neigh_off=0 if self.gcn else self.F,
+                            self_ids=None if self.gcn else fr, n_dev=self.n1_dev)
+        ops.encoder_fwd(comb1, self.w1, self.act1, h1, n_dev=self.n1_dev)
+        comb2, h2 = self.comb2[:b], self.h2[:b]
+        ops.gather_mean_fwd(self.h1, self.d1, idx2, cnt2, comb2, neigh_off=0 if self.gcn else self.d1,
+                            self_ids=None if self.gcn else self.self2[:b])
+        ops.encoder_fwd(comb2, self.w2, self.act2, h2)
+        ops.classifier_xent(h2, self.wc, labels, 1.0, self.logits[:b], self.loss, self.gh2[:b], self.gwc,
+                            ws=self.xent_ws)
+        ops.encoder_bwd(comb2, self.w2, h2, self.gh2[:b], self.act2, self.gw2, self.gcomb2[:b], dz=self.dz2,
+                        ws=self.ws)
+        gh1 = self.gh1[:n1_max]
+        gh1.zero_()
+        ops.scatter_mean_bwd(self.gcomb2[:b], self.d1, idx2, cnt2, self.gh1, neigh_off=0 if self.gcn else self.d1,
+                             self_ids=None if self.gcn else self.self2[:b])
+        ops.encoder_bwd(comb1, self.w1, h1, gh1, self.act1, self.gw1, None, dz=self.dz1, ws=self.ws,
+                        n_dev=self.n1_dev)
+        return n
+
+    def _update(self, lr):
+        ops.sgd_step(self.flat_w, self.flat_g, lr)
+        ops.advance_step(self.step_dev)
+
+    # ------------------------------------------------------------------ graph capture / replay
+    def _run(self, key, fn):
+        if not self.use_graphs:
+            fn()
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            if key not in self._warm:          # first call eager: loads kernels, sets func attributes
+                fn()
+                self._warm.add(key)
+                return
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                fn()
+            self._graphs[key] = g
+        g.replay()
+
+    def stage(self, nodes, labels, step):
+        """Host -> device copy of one minibatch's inputs (ids, labels, sampler step)."""
+        b = len(nodes)
+        if b > self.B:
+            raise ValueError("batch of %d exceeds the engine's max_batch %d" % (b, self.B))
+        h = self.stage_host
+        h[:8].view(torch.int64)[0] = int(step)
+        if isinstance(labels, torch.Tensor):
+            h[8:8 + 8 * b].view(torch.int64).copy_(labels.reshape(-1))
+        else:
+            h[8:8 + 8 * b].view(torch.int64).copy_(torch.from_numpy(np.asarray(labels, dtype=np.int64).reshape(-1)))
+        if isinstance(nodes, torch.Tensor):
+            h[8 + 8 * self.B:8 + 8 * self.B + 4 * b].view(torch.int32).copy_(nodes.reshape(-1))
+        else:
+            h[8 + 8 * self.B:8 + 8 * self.B + 4 * b].view(torch.int32).copy_(
+                torch.from_numpy(np.asarray(nodes, dtype=np.int32)))
+        self.stage_dev.copy_(h, non_blocking=True)
+        return b
+
+    def forward_backward(self, b):
+        self._run(("fb", b), lambda: self._forward_backward(b))
+
+    def update(self, lr):
+        self._run(("sgd", float(lr)), lambda: self._update(lr))
+
+    def train_step(self, b, lr, allreduce=None):
+        """fwd + bwd (+ gradient all-reduce) + SGD on the staged batch; returns nothing (the
+        loss stays in ``self.loss`` on the device)."""
+        if allreduce is None:
+            self._run(("step", b, float(lr)), lambda: (self._forward_backward(b), self._update(lr)))
+        else:
+            self.forward_backward(b)
+            allreduce(self.flat_g)
+            self.update(lr)
+
+    def read_loss(self):
+        self.loss_host.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_host[0])
+
+
+class _EngineLoss(torch.autograd.Function):
+    """Hands the engine's already-computed gradients to autograd, so that the reference's
+    ``loss.backward(); optimizer.step()`` (model.py:249-250) keeps working unchanged."""
+
+    @staticmethod
+    def forward(ctx, loss_buf, wc, w2, w1, gwc, gw2, gw1):
+        ctx.save_for_backward(gwc, gw2, gw1)
+        return loss_buf[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        gwc, gw2, gw1 = ctx.saved_tensors
+        return None, gwc * g, gw2 * g, gw1 * g, None, None, None
+
+
+def _closure_reaches(fn, target):
+    cells = getattr(fn, "__closure__", None) or ()
+    for c in cells:
+        try:
+            if c.cell_contents is target:
+                return True
+        except ValueError:
+            pass
+    return False
+
+
+def engine_for(model, batch):
+    """Return a TrainEngine bound to ``model`` (a SupervisedGraphSage) if its module tree is the
+    canonical 2-layer wiring over a frozen nn.Embedding table, else None.  The module
+    parameters are re-pointed at the engine's flat parameter block (same values)."""
+    import torch.nn as nn
+    from .aggregators import MeanAggregator, TABLE_INITIALIZERS
+    from .encoders import Encoder
+    eng = getattr(model, "_engine", None)
+    if eng is not None and eng.B >= batch and eng.k1 == model.enc.base_model.num_sample \
+            and eng.k2 == model.enc.num_sample:
+        return eng
+    enc2 = model.enc
+    enc1 = getattr(enc2, "base_model", None)
+    if not (isinstance(enc2, Encoder) and isinstance(enc1, Encoder)):
+        return None
+    agg1, agg2 = enc1.aggregator, enc2.aggregator
+    if not (isinstance(agg1, MeanAggregator) and isinstance(agg2, MeanAggregator)):
+        return None
+    emb = enc1.features
+    if not (isinstance(emb, nn.Embedding) and not emb.weight.requires_grad and agg1.features is emb):
+        return None
+    if enc1.initializer in TABLE_INITIALIZERS or enc2.initializer in TABLE_INITIALIZERS:
+        return None
+    if not (_closure_reaches(enc2.features, enc1) and _closure_reaches(agg2.features, enc1)):
+        return None
+    if enc1.gcn != enc2.gcn or getattr(enc1, "base_model", None) is not None:
+        return None
+    act = lambda e: ops.ACT_SIGMOID if e.initializer in _SIGMOID else ops.ACT_RELU
+    eng = TrainEngine(enc1.graph, enc2.graph, emb.weight.data, enc1.feat_dim, enc1.embed_dim, enc2.embed_dim,
+                      model.weight.shape[0], enc1.num_sample, enc2.num_sample, max(batch, 1), gcn=enc1.gcn,
+                      agg_gcn1=agg1.gcn, agg_gcn2=agg2.gcn, act1=act(enc1), act2=act(enc2),
+                      uid1=agg1.uid, uid2=agg2.uid)
+    with torch.no_grad():
+        for view, p in ((eng.w1, enc1.weight), (eng.w2, enc2.weight), (eng.wc, model.weight)):
+            view.copy_(p.data)
+            p.data = view
+    model._engine = eng
+    return eng

@@ -32,6 +32,35 @@ class SupervisedGraphSage(nn.Module):
             return labels.to(device=_device(), dtype=torch.int64).reshape(-1).contiguous()
         return torch.from_numpy(np.ascontiguousarray(np.asarray(labels, dtype=np.int64)).reshape(-1)).to(_device())
 
+    use_engine = None       # None: automatic (fused engine when the wiring is canonical); False: never
+
     def loss(self, nodes, labels):
+        """model.py:67-69.  With the canonical 2-layer wiring and autograd enabled the whole
+        step runs through the fused engine (engine.py) -- same kernels, same sampler draws as
+        the op-by-op path below -- and the returned scalar carries the gradients."""
+        if self.use_engine is not False and torch.is_grad_enabled():
+            from .engine import engine_for, _EngineLoss
+            eng = engine_for(self, len(nodes))
+            if eng is not None:
+                from . import sampling
+                with sampling.top_level_call() as step:
+                    b = eng.stage(nodes, labels, step)
+                    eng.forward_backward(b)
+                enc2 = self.enc
+                return _EngineLoss.apply(eng.loss, self.weight, enc2.weight, enc2.base_model.weight,
+                                         eng.gwc, eng.gw2, eng.gw1)
         embeds = self.enc(nodes)
-        return SoftmaxXent.apply(embeds.t(), self.weight, self._labels(labels))   # model.py:67-69
+        return SoftmaxXent.apply(embeds.t(), self.weight, self._labels(labels))
+
+    def train_step(self, nodes, labels, lr=0.7):
+        """The reference's timed unit (model.py:246-250: zero_grad, loss, backward, SGD step) as
+        one fused call; returns the loss as a Python float (one 4-byte device->host read)."""
+        from .engine import engine_for
+        from . import sampling
+        eng = engine_for(self, len(nodes))
+        if eng is None:
+            raise RuntimeError("train_step needs the canonical 2-layer wiring (model.py:214-227)")
+        with sampling.top_level_call() as step:
+            b = eng.stage(nodes, labels, step)
+            eng.train_step(b, lr)
+        return eng.read_loss()

@@ -143,7 +143,7 @@ def encoder_bwd(x, w, h, gh, act, gw, gx=None, dz=None, ws=None, n_dev=None):
     n_max, k_in = x.shape
     d_out = w.shape[0]
     if dz is None:
-        dz = torch.empty((max(n_max, 1), d_out), device=x.device, dtype=torch.float32)
+        dz = torch.empty((max(n_max, 1), round4(d_out)), device=x.device, dtype=torch.float32)
     if ws is None:
         ws = torch.empty(max(encoder_bwd_ws_floats(n_max, k_in, d_out), 4), device=x.device, dtype=torch.float32)
     N.check(lib.gs_encoder_bwd(N.ptr(x), x.stride(0), N.ptr(w), w.stride(0), N.ptr(h), h.stride(0),

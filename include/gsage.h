@@ -110,7 +110,7 @@ GS_API int gs_encoder_fwd(const float* x, int64_t ld_x, const float* w, int64_t 
                    float* h, int64_t ld_h, void* stream);
 
 /* Backward of the above (autograd ThresholdBackward/SigmoidBackward + MmBackward):
- *   dz = gh * act'(h)                      (written to dz [n_max, d_out], ld = d_out)
+ *   dz = gh * act'(h)                      (written to dz [n_max, round_up(d_out,4)])      
  *   gw[d_out, k_in]  = dz^T . x            (overwritten; split-K partials in ws)
  *   gx[n, k_in]      = dz . w              (only if gx != NULL)
  * ws must hold gs_encoder_bwd_ws_floats(n_max, k_in, d_out) floats.                      */
