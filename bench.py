@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""Benchmark of the sample -> aggregate -> update hot path (BASELINE.json metric:
+"target nodes/sec, 2-layer SAGE-mean fwd+bwd, 1/2/4/8 B200; gather HBM GB/s").
+
+    python bench.py --gpus 1 --steps 50 --warmup 10
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1
+
+Workload (SURVEY.md s8d, config 4 of BASELINE.json): synthetic Reddit-shape graph -- 233 000
+nodes, 5.8 M random undirected pairs (CSR ~11.6 M entries), 602-d fp32 features, 41 classes,
+2-layer SAGE-mean (concat), hidden 128/128, fan-out 25 at the targets / 10 at hop 1, B targets
+per GPU per step, SGD.  One "step" = sampling + forward + backward + SGD update of one batch
+(the unit timed at graphsage/model.py:245-252 of the reference).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "graphsage-simple_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "target nodes/sec, 2-layer SAGE-mean fwd+bwd"
+UNIT = "target nodes/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="targets per GPU per step")
+    ap.add_argument("--nodes", type=int, default=233000)
+    ap.add_argument("--pairs", type=int, default=5800000)
+    ap.add_argument("--feat", type=int, default=602)
+    ap.add_argument("--hidden", type=int, default=128)
+    ap.add_argument("--classes", type=int, default=41)
+    ap.add_argument("--k1", type=int, default=10, help="fan-out at hop 1 (inner layer)")
+    ap.add_argument("--k2", type=int, default=25, help="fan-out at the targets (outer layer)")
+    ap.add_argument("--lr", type=float, default=0.01,
+                    help="SGD lr (reference uses 0.7; 0.01 keeps long runs on random labels finite)")
+    ap.add_argument("--cpu-batch", type=int, default=256, help="targets per step of the CPU baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-profile", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ workload
+def build_graph_arrays(n, pairs):
+    """Reddit-shape synthetic graph of SURVEY.md s8d: default_rng(1) pairs, symmetrised,
+    deduplicated, rows sorted; every node has degree >= 1 with these sizes."""
+    rng = np.random.default_rng(1)
+    e = rng.integers(0, n, (2, pairs), dtype=np.int64)
+    src = np.concatenate([e[0], e[1]])
+    dst = np.concatenate([e[1], e[0]])
+    key = np.unique(src * np.int64(n) + dst)
+    s = key // n
+    d = (key - s * n).astype(np.int32)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(s, minlength=n), out=rowptr[1:])
+    return rowptr, d
+
+
+class LazyAdj(dict):
+    """``adj_lists`` view of a CSR for the CPU oracle: builds each node's set on first access
+    (inserting ids in ascending order) instead of materialising 11.6 M Python ints up front."""
+
+    def __init__(self, rowptr, col):
+        super().__init__()
+        self.rowptr, self.col = rowptr, col
+
+    def __missing__(self, v):
+        s = set(self.col[self.rowptr[v]:self.rowptr[v + 1]].tolist())
+        self[v] = s
+        return s
+
+
+def cpu_reference_rate(args, rowptr, col, table, labels, w1, w2, wc, batch, steps, warmup=1):
+    """Time the oracle port of the reference's CPU path (dense-mask formulation, Python
+    sampling) on this box's host cores.  Returns (targets/s, cores, description)."""
+    import random
+    import torch
+    from oracle import ref_path as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    adj = LazyAdj(rowptr, col)
+    model = R.TwoLayerModel(table, adj, adj, args.hidden, args.hidden, args.classes, args.k1, args.k2,
+                            gcn=False, w1=w1, w2=w2, wc=wc)
+    random.seed(1)
+    rng = np.random.default_rng(7)
+    times = []
+    for it in range(warmup + steps):
+        nodes = rng.integers(0, args.nodes, batch)
+        t0 = time.perf_counter()
+        model.train_step(list(nodes), labels[nodes], lr=args.lr)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    med = float(np.median(times))
+    return batch / med, cores, "B=%d targets/step, %d warm-up + %d timed steps, median %.3f s/step" % (
+        batch, warmup, steps, med)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    rowptr, col = build_graph_arrays(args.nodes, args.pairs)
+    torch.manual_seed(1)
+    table = torch.randn(args.nodes, args.feat)
+    labels = np.random.default_rng(1).integers(0, args.classes, (args.nodes, 1)).astype(np.int64)
+    ws = []
+    for shape in ((args.hidden, 2 * args.feat), (args.hidden, 2 * args.hidden), (args.classes, args.hidden)):
+        w = torch.empty(shape)
+        torch.nn.init.xavier_uniform_(w)
+        ws.append(w)
+    t0 = time.perf_counter()
+    rate, cores, sample = cpu_reference_rate(args, rowptr, col, table, labels, *ws, batch=args.cpu_batch,
+                                             steps=max(args.steps, 1), warmup=max(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.cpu_batch / rate,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, args.cpu_batch),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line))
+
+
+def workload_config(args, batch):
+    return {"workload": "synthetic Reddit-shape graph: %d nodes, %d undirected pairs (CSR ~2x), %d-d fp32 "
+                        "features, %d classes, 2-layer SAGE-mean concat, hidden %d/%d, fan-out %d (targets) / "
+                        "%d (hop-1), SGD" % (args.nodes, args.pairs, args.feat, args.classes, args.hidden,
+                                            args.hidden, args.k2, args.k1),
+            "batch_per_gpu": batch, "global_batch": batch * max(args.gpus, 1),
+            "parallelism": "dp%d (graph + features replicated, NCCL all-reduce of weight grads)" % args.gpus,
+            "l2_policy": "inputs larger than L2: 561 MB feature table, fresh random targets every step",
+            "lr": args.lr}
+
+
+# ------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import torch.nn as nn
+    from graphsage import ops, sampling
+    from graphsage.aggregators import MeanAggregator
+    from graphsage.encoders import Encoder
+    from graphsage.graph import CSRGraph
+    from graphsage.model import SupervisedGraphSage
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    rowptr, col = build_graph_arrays(args.nodes, args.pairs)
+    graph = CSRGraph(rowptr, col, dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1)
+    table = ops.empty_rows(args.nodes, args.feat, dev, zero=True)
+    table.copy_(torch.randn(args.nodes, args.feat, device=dev, generator=gen))
+    labels_np = np.random.default_rng(1).integers(0, args.classes, (args.nodes, 1)).astype(np.int64)
+
+    emb = nn.Embedding(args.nodes, args.feat, device="meta")
+    emb.weight = nn.Parameter(table, requires_grad=False)                  # model.py:214-215
+    torch.manual_seed(1)
+    agg1 = MeanAggregator(emb, cuda=True)
+    enc1 = Encoder(emb, args.feat, args.hidden, graph, agg1, num_sample=args.k1, gcn=False, cuda=True)
+    agg2 = MeanAggregator(lambda nodes: enc1(nodes).t(), cuda=True)
+    enc2 = Encoder(lambda nodes: enc1(nodes).t(), enc1.embed_dim, args.hidden, graph, agg2, num_sample=args.k2,
+                   base_model=enc1, gcn=False, cuda=True)
+    model = SupervisedGraphSage(args.classes, enc2)
+    sampling.seed(1)
+    w0 = [p.detach().cpu().clone() for p in (enc1.weight, enc2.weight, model.weight)]
+
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    rng = np.random.default_rng(100 + rank)
+    pool = K + W + 8
+    pool_nodes = rng.integers(0, args.nodes, (pool, B)).astype(np.int32)
+    pool_labels = labels_np[pool_nodes.reshape(-1)].reshape(pool, B)
+    from graphsage.engine import engine_for
+    eng = engine_for(model, B)
+    assert eng is not None, "canonical wiring not recognised"
+    allreduce = None
+    lr = args.lr
+    if world > 1:
+        allreduce = lambda flat: dist.all_reduce(flat)
+        lr = args.lr / world               # mean over the global batch = sum of rank means / world
+
+    # ---- (1) device-resident throughput: inputs already in HBM, one graph replay per step
+    d_nodes = torch.from_numpy(pool_nodes).to(dev)
+    d_labels = torch.from_numpy(pool_labels).to(dev)
+
+    def device_step(i):
+        eng.targets.copy_(d_nodes[i % pool])
+        eng.labels.copy_(d_labels[i % pool])
+        eng.train_step(B, lr, allreduce)
+
+    eng.stage(pool_nodes[0], pool_labels[0], 1)
+    for i in range(W + 3):                 # includes the eager + capture iterations
+        device_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        device_step(W + 3 + i)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * K / (ms_total / 1e3)
+    n1 = int(eng.n1_dev.item())
+    s1 = int(eng.cnt1[:n1].sum().item())
+    s2 = int(eng.cnt2[:B].sum().item())
+    loss_dev = float(eng.loss.item())
+
+    # ---- (2) end to end through the public API with host buffers (ids + labels H2D, loss D2H)
+    def e2e_step(i):
+        return model.train_step(pool_nodes[i % pool], pool_labels[i % pool], lr=lr) if world == 1 else \
+            e2e_step_dp(i)
+
+    def e2e_step_dp(i):
+        with sampling.top_level_call() as step:
+            b = eng.stage(pool_nodes[i % pool], pool_labels[i % pool], step)
+            eng.train_step(b, lr, allreduce)
+        return eng.read_loss()
+
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0.record()
+    for i in range(K):
+        e2e_loss = e2e_step(3 + i)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(t.item()) / 1e3)
+    clocks.stop_flag = True
+    clocks.join()
+
+    # ---- (3) drop-in API exactly as the reference's loop writes it (model.py:245-250)
+    api_value = None
+    if world == 1:
+        opt = torch.optim.SGD(filter(lambda p: p.requires_grad, model.parameters()), lr=lr)
+        lab_t = [torch.LongTensor(pool_labels[i]) for i in range(pool)]
+        node_l = [list(pool_nodes[i]) for i in range(pool)]
+        for i in range(3):
+            opt.zero_grad(); loss = model.loss(node_l[i], lab_t[i]); loss.backward(); opt.step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            opt.zero_grad()
+            loss = model.loss(node_l[(3 + i) % pool], lab_t[(3 + i) % pool])
+            loss.backward()
+            opt.step()
+            loss.item()
+        torch.cuda.synchronize()
+        api_value = B * K / (time.perf_counter() - t0)
+
+    # ---- (4) per-kernel times (eager launches, CUDA events around each C-ABI call)
+    kernels, roofline = None, None
+    if rank == 0 and not args.no_kernel_profile:
+        kernels = profile_kernels(eng, B, lr, d_nodes, d_labels)
+        import json as _j
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak, which = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        if os.path.exists(peaks_path):
+            peak, which = float(_j.load(open(peaks_path))["hbm_gbs"]), "measured copy bandwidth (MEASURED_PEAKS.json)"
+        g1_bytes = (s1 + n1) * args.feat * 4 + (s1 + 2 * n1) * 4 + n1 * 2 * args.feat * 4
+        g1_ms = kernels["gather_mean_fwd[layer1]"]
+        ach = g1_bytes / (g1_ms * 1e-3) / 1e9
+        roofline = {"kernel": "gather_mean_kernel (layer 1: self row + mean of k1 neighbour rows -> comb1)",
+                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "peak_source": which, "traffic": None,
+                    "algorithmic_bytes_per_launch": g1_bytes,
+                    "rows_read": s1 + n1, "n1": n1, "s1": s1, "s2": s2, "avg_launch_ms": g1_ms,
+                    "step_share": g1_ms / sum(kernels.values())}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, cores, sample = cpu_reference_rate(args, rowptr, col, table[:, :args.feat].cpu().contiguous(), labels_np,
+                                                 *w0, batch=args.cpu_batch, steps=args.cpu_steps)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(args, B),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 + 12 * B, "d2h_bytes_per_step": 4,
+                        "api": "SupervisedGraphSage.train_step(host ids, host labels) -> float loss",
+                        "reference_loop_api": api_value},
+                "gpu_launches": eng.launches_per_step * K if hasattr(eng, "launches_per_step") else None,
+                "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu, "kernels_ms": kernels,
+                "loss": loss_dev, "e2e_last_loss": e2e_loss}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_kernels(eng, B, lr, d_nodes, d_labels, iters=5):
+    """Average device time of every C-ABI call of one step, measured with CUDA events on the
+    launching stream (eager launches, not under a profiler)."""
+    import torch
+    from graphsage import ops
+    names, totals = [], {}
+    orig = {}
+    stack = []
+
+    def wrap(name):
+        fn = getattr(ops, name)
+        orig[name] = fn
+
+        def timed(*a, **kw):
+            label = name
+            if name in ("gather_mean_fwd", "encoder_fwd", "encoder_bwd", "sample_csr", "encoder_fwd_tc",
+                        "encoder_wgrad_tc"):
+                label += "[layer1]" if (kw.get("n_dev") is not None) else "[layer2]"
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **kw)
+            e1.record()
+            stack.append((label, e0, e1))
+            return out
+        setattr(ops, name, timed)
+
+    for nm in ("sample_csr", "dedup_remap", "gather_mean_fwd", "encoder_fwd", "encoder_fwd_tc", "classifier_xent",
+               "encoder_bwd", "encoder_wgrad_tc", "scatter_mean_bwd", "sgd_step", "advance_step"):
+        wrap(nm)
+    try:
+        for it in range(iters + 1):
+            eng.targets.copy_(d_nodes[it])
+            eng.labels.copy_(d_labels[it])
+            stack.clear()
+            eng._forward_backward(B)
+            eng._update(lr)
+            torch.cuda.synchronize()
+            if it == 0:
+                continue
+            for label, e0, e1 in stack:
+                totals[label] = totals.get(label, 0.0) + e0.elapsed_time(e1)
+    finally:
+        for nm, fn in orig.items():
+            setattr(ops, nm, fn)
+    return {k: v / iters for k, v in totals.items()}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

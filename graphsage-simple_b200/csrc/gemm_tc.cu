@@ -1,0 +1,494 @@
+// K3 on the 5th-gen tensor cores: tcgen05.mma kind::tf32 with a 3-term hi/lo operand split
+// ("3xTF32": a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi, fp32 accumulation in TMEM), which keeps
+// the encoder within the 1e-5 fp32 parity bar that a single TF32 pass misses.
+//
+//   forward  (NT):  H[n, 128]      = act( X[n, K] . W[128, K]^T )          X = combined tile
+//   backward (TN):  dW[128, K]     = dZ[n, 128]^T . X[n, K]                split over n
+//
+// Replaces `F.relu(self.weight.mm(combined.t()))` (graphsage/encoders.py:58-61) and the
+// MmBackward that produces `enc.weight.grad` (graphsage/model.py:249) of the reference.
+//
+// Structure per CTA (192 threads, 1 CTA/SM, 3-stage ring, 64 KB/stage):
+//   warp 0      TMA producer   X raw tile + pre-split Y_hi/Y_lo tiles -> smem (SWIZZLE_128B)
+//   warps 2..5  splitter       X raw -> X_hi (in place) + X_lo, elementwise so layout-agnostic;
+//                              later the epilogue (TMEM -> registers -> global)
+//   warp 1      MMA issuer     one elected lane: 4 k-steps x 3 tcgen05.mma per stage,
+//                              tcgen05.commit frees the stage / publishes the accumulator
+#include <cuda.h>
+#include "gs_common.cuh"
+
+namespace {
+
+constexpr int kStages = 3;
+constexpr int kTile = 128;            // M and N of the UMMA tile (d_out == 128)
+constexpr int kChunk = 32;            // reduction elements per stage: 32 fp32 = one 128-B swizzle row
+constexpr int kOperandBytes = kTile * kChunk * 4;          // 16 KB
+constexpr int kStageBytes = 4 * kOperandBytes;             // X_hi, X_lo, Y_hi, Y_lo
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kThreads = 192;
+// The tensor core rounds toward zero when it adds a k-step into the fp32 accumulator: measured
+// bias ~1 ulp per tcgen05.mma (profiles/README.md), i.e. ~1e-5 relative after the 450 MMAs of a
+// K = 1204 row.  Spreading the hi.hi products over kMainAccs accumulators and keeping the two
+// 2^-11-sized correction products in their own accumulator cuts the number of roundings that
+// touch a large partial sum by 9x; the epilogue adds the accumulators in fp32 (round-to-nearest).
+constexpr int kMainAccs = 3;
+constexpr int kAccs = kMainAccs + 1;  // 4 x 128 columns = the SM's whole TMEM
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 format (version 1).
+//   K-major : rows of 128 B, 8-row groups SBO = 1024 B apart (LBO unused for one swizzle atom)
+//   MN-major: tf32 operands must use SWIZZLE_128B_BASE32B (32-B swizzle atoms, the layout TMA's
+//             SWIZZLE_128B_ATOM_32B writes): 128-B rows of 32 M/N elements, 4-deep k groups SBO = 512 B
+//             apart, 32-element blocks along M/N LBO apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                             uint32_t layout_type = 2u /* SWIZZLE_128B */) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+    d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B (16-B atoms), 1 = SWIZZLE_128B_BASE32B (32-B atoms)
+    return d;
+}
+
+// Instruction descriptor: D fp32, A/B tf32, M = N = 128, dense.
+__host__ __device__ constexpr uint32_t make_idesc(bool mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((mn_major ? 1u : 0u) << 15) | ((mn_major ? 1u : 0u) << 16) |
+           ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    // hi = x rounded to nearest tf32 (10 explicit mantissa bits); lo = x - hi is exact in fp32
+    const uint32_t b = __float_as_uint(x);
+    hi = __uint_as_float((b + 0x1000u) & 0xFFFFE000u);
+    lo = x - hi;
+}
+
+struct TcArgs {
+    int n_max;                 // rows of X / dZ the grid was sized for
+    const int32_t* n_dev;      // optional device row count
+    int k_in;                  // columns of X
+    int act;
+    float* out;                // NT: h [n, 128]; TN: partials [splits][128][ld_out]
+    int64_t ld_out;
+    int rows_per_split;        // TN only (multiple of kChunk)
+    int64_t split_stride;      // TN only
+};
+
+template <bool TN>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_yhi,
+               const __grid_constant__ CUtensorMap map_ylo, TcArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + kStages * kStageBytes;        // full[3] ready[3] empty[3] accum
+    const uint32_t tmem_slot = bars + 128;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int n = gs_row_count(g.n_max, g.n_dev);
+    int chunk_begin, chunk_end, x_fixed;
+    if (!TN) {
+        x_fixed = blockIdx.x * kTile;                          // first row of this tile
+        if (x_fixed >= n) return;
+        chunk_begin = 0;
+        chunk_end = (g.k_in + kChunk - 1) / kChunk;            // over columns of X
+    } else {
+        x_fixed = blockIdx.x * kTile;                          // first column of this tile
+        const int r0 = blockIdx.y * g.rows_per_split;
+        const int r1 = min(n, r0 + g.rows_per_split);
+        chunk_begin = r0 / kChunk;
+        chunk_end = r1 > r0 ? (r1 + kChunk - 1) / kChunk : chunk_begin;   // over rows of X
+    }
+    const int nchunks = chunk_end - chunk_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bars + 8 * s, 1);                        // full: producer's expect_tx arrive
+            mbar_init(bars + 8 * (kStages + s), 4);            // ready: one arrive per splitter warp
+            mbar_init(bars + 8 * (2 * kStages + s), 1);        // empty: tcgen05.commit
+        }
+        mbar_init(bars + 8 * 3 * kStages, 1);                  // accumulator complete
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                           // TMEM: 4 accumulators of 128 fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kAccs * kTile));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + kStages * kStageBytes + 128);
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        if (lane == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % kStages, it = c / kStages;
+                mbar_wait(bars + 8 * (2 * kStages + s), (it & 1) ^ 1);
+                const uint32_t st = base + s * kStageBytes;
+                const uint32_t full = bars + 8 * s;
+                mbar_expect_tx(full, 3 * kOperandBytes);
+                const int kc = (chunk_begin + c) * kChunk;
+                if (!TN) {
+                    tma_load_2d(st, &map_x, kc, x_fixed, full);                           // X rows, cols kc..
+                    tma_load_2d(st + 2 * kOperandBytes, &map_yhi, kc, 0, full);           // W_hi
+                    tma_load_2d(st + 3 * kOperandBytes, &map_ylo, kc, 0, full);           // W_lo
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {                                         // 32-column blocks
+                        tma_load_2d(st + b * 4096, &map_x, x_fixed + 32 * b, kc, full);
+                        tma_load_2d(st + 2 * kOperandBytes + b * 4096, &map_yhi, 32 * b, kc, full);
+                        tma_load_2d(st + 3 * kOperandBytes + b * 4096, &map_ylo, 32 * b, kc, full);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        constexpr uint32_t idesc = make_idesc(TN);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % kStages, it = c / kStages;
+            mbar_wait(bars + 8 * s, it & 1);                   // TMA bytes (Y tiles) landed
+            mbar_wait(bars + 8 * (kStages + s), it & 1);       // X split done
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t st = base + s * kStageBytes;
+                const uint32_t x_hi = st, x_lo = st + kOperandBytes, y_hi = st + 2 * kOperandBytes,
+                               y_lo = st + 3 * kOperandBytes;
+#pragma unroll
+                for (int j = 0; j < kChunk / 8; ++j) {         // UMMA_K = 8 for tf32
+                    uint64_t dxh, dxl, dyh, dyl;
+                    if (!TN) {                                 // K-major: advance 32 B inside the swizzle row
+                        dxh = make_desc(x_hi + 32 * j, 16, 1024); dxl = make_desc(x_lo + 32 * j, 16, 1024);
+                        dyh = make_desc(y_hi + 32 * j, 16, 1024); dyl = make_desc(y_lo + 32 * j, 16, 1024);
+                    } else {                                   // MN-major: advance one 8-deep k group
+                        dxh = make_desc(x_hi + 1024 * j, 4096, 512, 1u); dxl = make_desc(x_lo + 1024 * j, 4096, 512, 1u);
+                        dyh = make_desc(y_hi + 1024 * j, 4096, 512, 1u); dyl = make_desc(y_lo + 1024 * j, 4096, 512, 1u);
+                    }
+                    const int ks = c * (kChunk / 8) + j;       // k-step index within this CTA
+                    const uint32_t d_main = tmem + (uint32_t)(ks % kMainAccs) * kTile;
+                    const uint32_t d_corr = tmem + (uint32_t)kMainAccs * kTile;
+                    const uint32_t acc_main = ks >= kMainAccs ? 1u : 0u, acc_corr = ks ? 1u : 0u;
+                    if (!TN) {                                 // A = X (rows), B = W
+                        umma_tf32(d_corr, dxl, dyh, idesc, acc_corr);
+                        umma_tf32(d_corr, dxh, dyl, idesc, 1u);
+                        umma_tf32(d_main, dxh, dyh, idesc, acc_main);
+                    } else {                                   // A = dZ^T (d_out), B = X (cols)
+                        umma_tf32(d_corr, dyl, dxh, idesc, acc_corr);
+                        umma_tf32(d_corr, dyh, dxl, idesc, 1u);
+                        umma_tf32(d_main, dyh, dxh, idesc, acc_main);
+                    }
+                }
+                umma_commit(bars + 8 * (2 * kStages + s));     // stage reusable once these MMAs retire
+                if (c == nchunks - 1) umma_commit(bars + 8 * 3 * kStages);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------------------------------------------------------- splitter + epilogue
+        const int t = threadIdx.x - 64;                        // 0..127
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % kStages, it = c / kStages;
+            mbar_wait(bars + 8 * s, it & 1);
+            float4* xh = reinterpret_cast<float4*>(gen_base + s * kStageBytes);
+            float4* xl = reinterpret_cast<float4*>(gen_base + s * kStageBytes + kOperandBytes);
+#pragma unroll
+            for (int u = 0; u < kOperandBytes / 16 / 128; ++u) {
+                const int e = t + u * 128;
+                const float4 v = xh[e];
+                float4 h, l;
+                split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+                split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                xh[e] = h;
+                xl[e] = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor core reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 8 * (kStages + s));
+        }
+        if (nchunks > 0) {
+            mbar_wait(bars + 8 * 3 * kStages, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const int q = warp & 3;                                // TMEM lane quadrant this warp may read
+        const int row = q * 32 + lane;                         // accumulator row (lane of TMEM)
+#pragma unroll 1
+        for (int cb = 0; cb < kTile / 32; ++cb) {
+            uint32_t r[32];
+            if (nchunks > 0) {                                 // sum the 4 accumulators in fp32 (RN)
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb * 32, r);
+#pragma unroll 1
+                for (int a = 1; a < kAccs; ++a) {
+                    uint32_t t2[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + a * kTile + cb * 32, t2);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(t2[i]));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = 0u;
+            }
+            if (!TN) {
+                const int grow = x_fixed + row;
+                if (grow < n) {
+                    float* dst = g.out + (int64_t)grow * g.ld_out + cb * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 v = make_float4(gs_apply_act(__uint_as_float(r[i]), g.act),
+                                               gs_apply_act(__uint_as_float(r[i + 1]), g.act),
+                                               gs_apply_act(__uint_as_float(r[i + 2]), g.act),
+                                               gs_apply_act(__uint_as_float(r[i + 3]), g.act));
+                        *reinterpret_cast<float4*>(dst + i) = v;
+                    }
+                }
+            } else {
+                float* dst = g.out + (int64_t)blockIdx.y * g.split_stride + (int64_t)row * g.ld_out + x_fixed + cb * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const int col = x_fixed + cb * 32 + i;
+                    if (col + 4 <= g.k_in) {
+                        *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                                         __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                    } else {
+                        for (int e = 0; e < 4; ++e)
+                            if (col + e < g.k_in) dst[i + e] = __uint_as_float(r[i + e]);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kAccs * kTile));
+    }
+}
+
+// W -> (W_hi, W_lo) and dz = gh * act'(h) -> (dz_hi, dz_lo): the pre-split "Y" operands.
+__global__ void split_rows_kernel(const float* __restrict__ src, int64_t ld_src, int rows, int cols,
+                                  float* __restrict__ hi, float* __restrict__ lo, int64_t ld_dst) {
+    const int64_t total = (int64_t)rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / cols), c = (int)(e - (int64_t)r * cols);
+        float h, l;
+        split_tf32(src[(int64_t)r * ld_src + c], h, l);
+        hi[(int64_t)r * ld_dst + c] = h;
+        lo[(int64_t)r * ld_dst + c] = l;
+    }
+}
+
+__global__ void act_grad_split_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restrict__ gh, int64_t ld_gh,
+                                      int d, int act, int n_max, const int32_t* __restrict__ n_dev,
+                                      float* __restrict__ hi, float* __restrict__ lo) {
+    const int n = gs_row_count(n_max, n_dev);
+    const int64_t total = (int64_t)n_max * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / d), j = (int)(e - (int64_t)i * d);
+        float a = 0.f, b = 0.f;
+        if (i < n) split_tf32(gh[(int64_t)i * ld_gh + j] * gs_act_grad(h[(int64_t)i * ld_h + j], act), a, b);
+        hi[e] = a;
+        lo[e] = b;
+    }
+}
+
+__global__ void tc_reduce_kernel(const float* __restrict__ ws, int splits, int64_t stride, int64_t ld_ws,
+                                 int M, int N, float* __restrict__ out, int64_t ld_out) {
+    const int64_t total = (int64_t)M * N;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(e / N), c = (int)(e - (int64_t)m * N);
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += ws[(int64_t)z * stride + (int64_t)m * ld_ws + c];
+        out[(int64_t)m * ld_out + c] = s;
+    }
+}
+
+// ---- host: tensor maps -------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// row-major fp32 [rows, cols] with leading dimension ld; box = box_cols x box_rows, SWIZZLE_128B
+int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+             CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return GS_ENOSUP;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GS_OK : GS_EINVAL;
+}
+
+int tn_splits(int n_max, int k_in) {
+    // enough splits to fill the SMs, and never more than kMaxChunksPerSplit stages accumulated in
+    // one CTA (bounds the round-toward-zero accumulation bias, see kMainAccs)
+    constexpr int kMaxChunksPerSplit = 32;
+    const int tiles = (k_in + kTile - 1) / kTile;
+    int s = (GS_NUM_SMS + tiles - 1) / tiles;
+    const int need = (n_max + kMaxChunksPerSplit * kChunk - 1) / (kMaxChunksPerSplit * kChunk);
+    if (s < need) s = need;
+    const int cap = (n_max + 4 * kChunk - 1) / (4 * kChunk);
+    if (s > cap) s = cap;
+    return s < 1 ? 1 : s;
+}
+
+int grid1d(int64_t total) {
+    int64_t b = (total + 255) / 256;
+    if (b > GS_NUM_SMS * 8) b = GS_NUM_SMS * 8;
+    return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+extern "C" int gs_encoder_tc_supported(int32_t k_in, int32_t d_out) {
+    return (d_out == kTile && k_in >= kChunk && (k_in & 3) == 0) ? 1 : 0;
+}
+
+// floats of workspace for the forward: W_hi + W_lo
+extern "C" int64_t gs_encoder_fwd_tc_ws_floats(int32_t k_in, int32_t d_out) {
+    return 2 * (int64_t)d_out * ((k_in + 3) & ~3);
+}
+
+extern "C" int gs_encoder_fwd_tc(const float* x, int64_t ld_x, const float* w, int64_t ld_w,
+                                 int32_t k_in, int32_t d_out, int32_t act,
+                                 int32_t n_max, const int32_t* n_dev,
+                                 float* h, int64_t ld_h, float* ws, void* stream) {
+    if (!x || !w || !h || !ws || n_max < 0) return GS_EINVAL;
+    if (!gs_encoder_tc_supported(k_in, d_out)) return GS_ENOSUP;
+    if (!gs_aligned16(x) || !gs_aligned16(w) || !gs_aligned16(h) || !gs_aligned16(ws) || (ld_x & 3) || (ld_w & 3) || (ld_h & 3))
+        return GS_EALIGN;
+    if (n_max == 0) return GS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t ldw = (k_in + 3) & ~3;
+    float* w_hi = ws;
+    float* w_lo = ws + (int64_t)d_out * ldw;
+    split_rows_kernel<<<grid1d((int64_t)d_out * k_in), 256, 0, s>>>(w, ld_w, d_out, k_in, w_hi, w_lo, ldw);
+    GS_LAUNCH_CHECK();
+    CUtensorMap mx, mh, ml;
+    int rc;
+    if ((rc = make_map(&mx, x, n_max, k_in, ld_x, kChunk, kTile))) return rc;
+    if ((rc = make_map(&mh, w_hi, d_out, k_in, ldw, kChunk, kTile))) return rc;
+    if ((rc = make_map(&ml, w_lo, d_out, k_in, ldw, kChunk, kTile))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    TcArgs g{n_max, n_dev, k_in, act, h, ld_h, 0, 0};
+    tc_gemm_kernel<false><<<(n_max + kTile - 1) / kTile, kThreads, kSmemBytes, s>>>(mx, mh, ml, g);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+// floats of workspace for the weight gradient: dz_hi + dz_lo + split-K partials
+extern "C" int64_t gs_encoder_wgrad_tc_ws_floats(int32_t n_max, int32_t k_in, int32_t d_out) {
+    const int64_t ldw = (k_in + 3) & ~3;
+    return 2 * (int64_t)(n_max > 0 ? n_max : 1) * d_out + (int64_t)tn_splits(n_max, k_in) * d_out * ldw;
+}
+
+extern "C" int gs_encoder_wgrad_tc(const float* x, int64_t ld_x, const float* h, int64_t ld_h,
+                                   const float* gh, int64_t ld_gh, int32_t k_in, int32_t d_out, int32_t act,
+                                   int32_t n_max, const int32_t* n_dev,
+                                   float* gw, int64_t ld_gw, float* ws, void* stream) {
+    if (!x || !h || !gh || !gw || !ws || n_max < 0) return GS_EINVAL;
+    if (!gs_encoder_tc_supported(k_in, d_out)) return GS_ENOSUP;
+    if (!gs_aligned16(x) || !gs_aligned16(ws) || (ld_x & 3)) return GS_EALIGN;
+    if (n_max == 0) return GS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t ldw = (k_in + 3) & ~3;
+    float* dz_hi = ws;
+    float* dz_lo = ws + (int64_t)n_max * d_out;
+    float* part = ws + 2 * (int64_t)n_max * d_out;
+    act_grad_split_kernel<<<grid1d((int64_t)n_max * d_out), 256, 0, s>>>(h, ld_h, gh, ld_gh, d_out, act, n_max, n_dev,
+                                                                        dz_hi, dz_lo);
+    GS_LAUNCH_CHECK();
+    const int splits = tn_splits(n_max, k_in);
+    int rps = (n_max + splits - 1) / splits;
+    rps = ((rps + kChunk - 1) / kChunk) * kChunk;
+    CUtensorMap mx, mh, ml;
+    int rc;
+    const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;    // MN-major tf32 operand layout
+    if ((rc = make_map(&mx, x, n_max, k_in, ld_x, 32, kChunk, swz))) return rc;
+    if ((rc = make_map(&mh, dz_hi, n_max, d_out, d_out, 32, kChunk, swz))) return rc;
+    if ((rc = make_map(&ml, dz_lo, n_max, d_out, d_out, 32, kChunk, swz))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    TcArgs g{n_max, n_dev, k_in, GS_ACT_NONE, part, ldw, rps, (int64_t)d_out * ldw};
+    dim3 grid((k_in + kTile - 1) / kTile, splits);
+    tc_gemm_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(mx, mh, ml, g);
+    GS_LAUNCH_CHECK();
+    tc_reduce_kernel<<<grid1d((int64_t)d_out * k_in), 256, 0, s>>>(part, splits, (int64_t)d_out * ldw, ldw, d_out, k_in,
+                                                                  gw, ld_gw);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}

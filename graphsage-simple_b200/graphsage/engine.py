@@ -82,6 +82,11 @@ class TrainEngine:
                  ops.encoder_bwd_ws_floats(B, self.K2, self.d2), 4)
         self.ws = torch.empty(ws, device=dev)
         self.xent_ws = torch.empty(B * self.C + B, device=dev)
+        # layer 1 runs on the tcgen05 path when the shape qualifies (d1 == 128, K1 % 4 == 0)
+        self.tc1 = ops.encoder_tc_supported(self.K1, self.d1)
+        if self.tc1:
+            self.tc_ws = torch.empty(max(ops.encoder_fwd_tc_ws_floats(self.K1, self.d1),
+                                         ops.encoder_wgrad_tc_ws_floats(n1_max, self.K1, self.d1)), device=dev)
         # parameters + gradients: one flat block each (padded rows), module params alias into it
         shapes = [(self.d1, self.K1), (self.d2, self.K2), (self.C, self.d2)]
         sizes = [r * ops.round4(c) for r, c in shapes]
@@ -96,7 +101,7 @@ class TrainEngine:
         self.gw1, self.gw2, self.gwc = views_g
         self._graphs = {}
         self._warm = set()
-        self.launches_per_step = 0
+        self._launch_count = {}
 
     # ------------------------------------------------------------------ the launch sequence
     def _forward_backward(self, b):
@@ -126,7 +131,10 @@ class TrainEngine:
         comb1, h1 = self.comb1[:n1_max], self.h1[:n1_max]
         ops.gather_mean_fwd(self.table, self.F, idx1, cnt1, comb1, neigh_off=0 if self.gcn else self.F,
                             self_ids=None if self.gcn else fr, n_dev=self.n1_dev)
-        ops.encoder_fwd(comb1, self.w1, self.act1, h1, n_dev=self.n1_dev)
+        if self.tc1:
+            ops.encoder_fwd_tc(comb1, self.w1, self.act1, h1, ws=self.tc_ws, n_dev=self.n1_dev)
+        else:
+            ops.encoder_fwd(comb1, self.w1, self.act1, h1, n_dev=self.n1_dev)
         comb2, h2 = self.comb2[:b], self.h2[:b]
         ops.gather_mean_fwd(self.h1, self.d1, idx2, cnt2, comb2, neigh_off=0 if self.gcn else self.d1,
                             self_ids=None if self.gcn else self.self2[:b])
@@ -139,8 +147,11 @@ class TrainEngine:
         gh1.zero_()
         ops.scatter_mean_bwd(self.gcomb2[:b], self.d1, idx2, cnt2, self.gh1, neigh_off=0 if self.gcn else self.d1,
                              self_ids=None if self.gcn else self.self2[:b])
-        ops.encoder_bwd(comb1, self.w1, h1, gh1, self.act1, self.gw1, None, dz=self.dz1, ws=self.ws,
-                        n_dev=self.n1_dev)
+        if self.tc1:
+            ops.encoder_wgrad_tc(comb1, h1, gh1, self.act1, self.gw1, ws=self.tc_ws, n_dev=self.n1_dev)
+        else:
+            ops.encoder_bwd(comb1, self.w1, h1, gh1, self.act1, self.gw1, None, dz=self.dz1, ws=self.ws,
+                            n_dev=self.n1_dev)
         return n
 
     def _update(self, lr):
@@ -155,7 +166,9 @@ class TrainEngine:
         g = self._graphs.get(key)
         if g is None:
             if key not in self._warm:          # first call eager: loads kernels, sets func attributes
+                before = ops.LAUNCHES[0]
                 fn()
+                self._launch_count[key] = ops.LAUNCHES[0] - before
                 self._warm.add(key)
                 return
             g = torch.cuda.CUDAGraph()
@@ -164,6 +177,15 @@ class TrainEngine:
                 fn()
             self._graphs[key] = g
         g.replay()
+
+    @property
+    def launches_per_step(self):
+        """Kernels of libgsage_sm100.so in one train step (fwd+bwd+SGD), counted when enqueued."""
+        c = self._launch_count
+        whole = [v for k, v in c.items() if k[0] == "step"]
+        if whole:
+            return max(whole)
+        return max([v for k, v in c.items() if k[0] == "fb"] or [0]) + max([v for k, v in c.items() if k[0] == "sgd"] or [0])
 
     def stage(self, nodes, labels, step):
         """Host -> device copy of one minibatch's inputs (ids, labels, sampler step)."""

@@ -7,6 +7,8 @@ from . import _native as N
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 
+LAUNCHES = [0]        # kernels of libgsage_sm100.so enqueued through this module (bench.py reports it)
+
 TAG_AGG2 = 2          # layer-2 aggregator over the targets        (RNG draw #2)
 TAG_AGG1_HOP = 1      # layer-1 aggregator over the hop-1 uniques  (RNG draw #1)
 TAG_AGG1_SELF = 3     # layer-1 aggregator over the batch nodes    (RNG draw #3)
@@ -67,6 +69,7 @@ def sample_csr(rowptr, col, num_nodes, nodes, k, add_self=False, seed=0, step=0,
                               kk, width, int(bool(add_self)), int(seed) & (2 ** 64 - 1), int(step), N.ptr(step_dev),
                               int(tag_head), int(tag_tail), int(n_head), N.ptr(idx), N.ptr(cnt), N.stream()),
             "gs_sample_csr")
+    LAUNCHES[0] += 1
     return idx, cnt
 
 
@@ -92,6 +95,7 @@ def dedup_remap(idx, cnt, scratch, slot_base=0, n_dev=None, uniq=None, n_total=N
     N.check(lib.gs_dedup_remap(N.ptr(idx), N.ptr(cnt), n_max, N.ptr(n_dev), width, scratch.num_nodes,
                                N.ptr(scratch.slot_of), N.ptr(scratch.block_counts), int(slot_base),
                                N.ptr(uniq), N.ptr(n_total), N.stream()), "gs_dedup_remap")
+    LAUNCHES[0] += 4
     return uniq, n_total
 
 
@@ -102,6 +106,7 @@ def gather_mean_fwd(table, dim, idx, cnt, out, neigh_off=0, self_ids=None, n_dev
     N.check(lib.gs_gather_mean_fwd(N.ptr(table), table.stride(0), int(dim), N.ptr(idx), N.ptr(cnt), width,
                                    N.ptr(self_ids), n_max, N.ptr(n_dev), N.ptr(out), out.stride(0),
                                    int(neigh_off), N.stream()), "gs_gather_mean_fwd")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -112,6 +117,7 @@ def scatter_mean_bwd(gout, dim, idx, cnt, gtable, neigh_off=0, self_ids=None, n_
     N.check(lib.gs_scatter_mean_bwd(N.ptr(gout), gout.stride(0), int(neigh_off), int(dim), N.ptr(idx), N.ptr(cnt),
                                     width, N.ptr(self_ids), n_max, N.ptr(n_dev), N.ptr(gtable), gtable.stride(0),
                                     N.stream()), "gs_scatter_mean_bwd")
+    LAUNCHES[0] += 1
     return gtable
 
 
@@ -120,6 +126,7 @@ def gather_rows(table, dim, ids, out, n_dev=None):
     N.require_cuda(table, ids, out)
     N.check(lib.gs_gather_rows(N.ptr(table), table.stride(0), int(dim), N.ptr(ids), ids.shape[0], N.ptr(n_dev),
                                N.ptr(out), out.stride(0), N.stream()), "gs_gather_rows")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -130,6 +137,7 @@ def encoder_fwd(x, w, act, h, n_dev=None):
     d_out = w.shape[0]
     N.check(lib.gs_encoder_fwd(N.ptr(x), x.stride(0), N.ptr(w), w.stride(0), k_in, d_out, int(act), n_max,
                                N.ptr(n_dev), N.ptr(h), h.stride(0), N.stream()), "gs_encoder_fwd")
+    LAUNCHES[0] += 1
     return h
 
 
@@ -150,7 +158,49 @@ def encoder_bwd(x, w, h, gh, act, gw, gx=None, dz=None, ws=None, n_dev=None):
                                N.ptr(gh), gh.stride(0), k_in, d_out, int(act), n_max, N.ptr(n_dev),
                                N.ptr(dz), N.ptr(gw), gw.stride(0), N.ptr(gx), gx.stride(0) if gx is not None else 0,
                                N.ptr(ws), N.stream()), "gs_encoder_bwd")
+    LAUNCHES[0] += 2 + (1 if gx is not None else 0) + (1 if encoder_bwd_ws_floats(n_max, k_in, d_out) > d_out * round4(k_in) else 0)
     return gw, gx
+
+
+def encoder_tc_supported(k_in, d_out):
+    return bool(N.load().gs_encoder_tc_supported(int(k_in), int(d_out)))
+
+
+def encoder_fwd_tc_ws_floats(k_in, d_out):
+    return int(N.load().gs_encoder_fwd_tc_ws_floats(int(k_in), int(d_out)))
+
+
+def encoder_wgrad_tc_ws_floats(n_max, k_in, d_out):
+    return int(N.load().gs_encoder_wgrad_tc_ws_floats(int(n_max), int(k_in), int(d_out)))
+
+
+def encoder_fwd_tc(x, w, act, h, ws=None, n_dev=None):
+    """K3 forward on tcgen05 (3xTF32) -- same contract as encoder_fwd."""
+    lib = N.load()
+    N.require_cuda(x, w, h)
+    n_max, k_in = x.shape
+    d_out = w.shape[0]
+    if ws is None:
+        ws = torch.empty(encoder_fwd_tc_ws_floats(k_in, d_out), device=x.device, dtype=torch.float32)
+    N.check(lib.gs_encoder_fwd_tc(N.ptr(x), x.stride(0), N.ptr(w), w.stride(0), k_in, d_out, int(act), n_max,
+                                  N.ptr(n_dev), N.ptr(h), h.stride(0), N.ptr(ws), N.stream()), "gs_encoder_fwd_tc")
+    LAUNCHES[0] += 2
+    return h
+
+
+def encoder_wgrad_tc(x, h, gh, act, gw, ws=None, n_dev=None):
+    """Weight gradient of K3 on tcgen05 (3xTF32): gw = (gh * act'(h))^T . x."""
+    lib = N.load()
+    N.require_cuda(x, h, gh, gw)
+    n_max, k_in = x.shape
+    d_out = h.shape[1]
+    if ws is None:
+        ws = torch.empty(encoder_wgrad_tc_ws_floats(n_max, k_in, d_out), device=x.device, dtype=torch.float32)
+    N.check(lib.gs_encoder_wgrad_tc(N.ptr(x), x.stride(0), N.ptr(h), h.stride(0), N.ptr(gh), gh.stride(0), k_in, d_out,
+                                    int(act), n_max, N.ptr(n_dev), N.ptr(gw), gw.stride(0), N.ptr(ws), N.stream()),
+            "gs_encoder_wgrad_tc")
+    LAUNCHES[0] += 3
+    return gw
 
 
 def classifier_xent(h, wc, labels, grad_scale=1.0, logits=None, loss=None, gh=None, gwc=None, ws=None):
@@ -165,6 +215,7 @@ def classifier_xent(h, wc, labels, grad_scale=1.0, logits=None, loss=None, gh=No
                                    N.ptr(loss), N.ptr(gh), gh.stride(0) if gh is not None else 0,
                                    N.ptr(gwc), gwc.stride(0) if gwc is not None else 0, N.ptr(ws), N.stream()),
             "gs_classifier_xent")
+    LAUNCHES[0] += 2
     return loss
 
 
@@ -173,8 +224,10 @@ def sgd_step(p, g, lr):
     N.require_cuda(p, g)
     assert p.is_contiguous() and g.is_contiguous() and p.numel() == g.numel()
     N.check(lib.gs_sgd_step(N.ptr(p), N.ptr(g), float(lr), p.numel(), N.stream()), "gs_sgd_step")
+    LAUNCHES[0] += 1
     return p
 
 
 def advance_step(step_dev):
     N.check(N.load().gs_advance_step(N.ptr(step_dev), N.stream()), "gs_advance_step")
+    LAUNCHES[0] += 1

@@ -122,6 +122,23 @@ GS_API int gs_encoder_bwd(const float* x, int64_t ld_x, const float* w, int64_t 
                    float* dz, float* gw, int64_t ld_gw, float* gx, int64_t ld_gx,
                    float* ws, void* stream);
 
+/* ---- K3 on tcgen05 tensor cores (3xTF32, fp32 accumulation in TMEM) ------------------------
+ * Same contracts as gs_encoder_fwd and the gw part of gs_encoder_bwd, for the shapes
+ * gs_encoder_tc_supported() accepts (d_out == 128, k_in % 4 == 0).  The three-term hi/lo
+ * TF32 split keeps results within 1e-5 (norm-wise) of the fp32 reference path.
+ * ws: gs_encoder_fwd_tc_ws_floats / gs_encoder_wgrad_tc_ws_floats floats, 16-B aligned.    */
+GS_API int gs_encoder_tc_supported(int32_t k_in, int32_t d_out);
+GS_API int64_t gs_encoder_fwd_tc_ws_floats(int32_t k_in, int32_t d_out);
+GS_API int gs_encoder_fwd_tc(const float* x, int64_t ld_x, const float* w, int64_t ld_w,
+                      int32_t k_in, int32_t d_out, int32_t act,
+                      int32_t n_max, const int32_t* n_dev,
+                      float* h, int64_t ld_h, float* ws, void* stream);
+GS_API int64_t gs_encoder_wgrad_tc_ws_floats(int32_t n_max, int32_t k_in, int32_t d_out);
+GS_API int gs_encoder_wgrad_tc(const float* x, int64_t ld_x, const float* h, int64_t ld_h,
+                        const float* gh, int64_t ld_gh, int32_t k_in, int32_t d_out, int32_t act,
+                        int32_t n_max, const int32_t* n_dev,
+                        float* gw, int64_t ld_gw, float* ws, void* stream);
+
 /* ---- K5: classifier + softmax cross-entropy, forward and backward -------------------------
  * Replaces `scores = self.weight.mm(embeds).t()` and nn.CrossEntropyLoss (mean reduction),
  * graphsage/model.py:57, 62-69, and their autograd backward.

@@ -264,3 +264,44 @@ def test_sgd_step_bit_exact(ops):
 def test_cpu_tensors_are_rejected(ops):
     with pytest.raises(RuntimeError):
         ops.gather_rows(torch.zeros(4, 4), 4, torch.zeros(2, dtype=torch.int32), torch.zeros(2, 4))
+
+
+@pytest.mark.parametrize("n,k_in,act", [(1000, 1204, 1), (128, 32, 0), (333, 256, 1), (26000, 1204, 1), (2049, 600, 2),
+                                        (77, 1000, 1)])
+def test_encoder_tensor_core_path(ops, n, k_in, act):
+    """tcgen05 3xTF32 encoder GEMMs against an fp64 reference, same 1e-5 bar as the fp32 path."""
+    d_out = 128
+    assert ops.encoder_tc_supported(k_in, d_out)
+    g = torch.Generator(device="cuda").manual_seed(n + k_in)
+    x = ops.empty_rows(n, k_in, "cuda")
+    x.copy_(torch.randn(n, k_in, device="cuda", generator=g))
+    w = torch.randn(d_out, k_in, device="cuda", generator=g) / k_in ** 0.5
+    gh = torch.randn(n, d_out, device="cuda", generator=g)
+    h = torch.full((n, d_out), float("nan"), device="cuda")
+    ops.encoder_fwd_tc(x, w, act, h)
+    pre = x.double() @ w.double().t()
+    ref = {0: pre, 1: torch.relu(pre), 2: torch.sigmoid(pre)}[act]
+    assert relerr(h.cpu().numpy(), ref.cpu().numpy()) < REL
+    gw = torch.full((d_out, k_in), float("nan"), device="cuda")
+    ops.encoder_wgrad_tc(x, h, gh, act, gw)
+    hd = h.double()
+    dz = gh.double() * {0: torch.ones_like(hd), 1: (hd > 0).double(), 2: hd * (1 - hd)}[act]
+    assert relerr(gw.cpu().numpy(), (dz.t() @ x.double()).cpu().numpy()) < REL
+
+
+def test_encoder_tensor_core_device_row_count(ops):
+    n_max, n, k_in, d_out = 900, 517, 256, 128
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(n_max, k_in, device="cuda", generator=g)
+    w = torch.randn(d_out, k_in, device="cuda", generator=g) / 16
+    gh = torch.randn(n_max, d_out, device="cuda", generator=g)
+    n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
+    h = torch.full((n_max, d_out), 7.0, device="cuda")
+    ops.encoder_fwd_tc(x, w, 1, h, n_dev=n_dev)
+    ref = torch.relu(x[:n].double() @ w.double().t())
+    assert relerr(h[:n].cpu().numpy(), ref.cpu().numpy()) < REL
+    assert (h[(n + 127) // 128 * 128:] == 7.0).all()          # tiles past *n_dev are not touched
+    gw = torch.empty(d_out, k_in, device="cuda")
+    ops.encoder_wgrad_tc(x, h, gh, 1, gw, n_dev=n_dev)
+    dz = gh[:n].double() * (ref > 0)
+    assert relerr(gw.cpu().numpy(), (dz.t() @ x[:n].double()).cpu().numpy()) < REL
