@@ -84,34 +84,63 @@ xent_rows_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restr
     }
 }
 
-// gwc[c, :] = sum_i dl[i, c] * h[i, :]   (block per class, fixed order over i);
-// block 0 also reduces the per-row losses to the mean.
+// gwc[c, :] = sum_i dl[i, c] * h[i, :] in two fixed-order stages: grid (C, S) partial sums over
+// row slices, then one pass adding the S partials (which also reduces the per-row losses).
+constexpr int kWgradSplits = 16;
+
+__global__ void __launch_bounds__(128)
+xent_wgrad_partial_kernel(const float* __restrict__ h, int64_t ld_h, int d, int C, int n,
+                          const float* __restrict__ ws, float* __restrict__ part) {
+    const int c = blockIdx.x, z = blockIdx.y;
+    const int per = (n + kWgradSplits - 1) / kWgradSplits;
+    const int i0 = z * per, i1 = min(n, i0 + per);
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        float acc = 0.f;
+        int i = i0;
+        for (; i + 4 <= i1; i += 4) {
+            const float w0 = ws[(int64_t)i * C + c], w1 = ws[(int64_t)(i + 1) * C + c];
+            const float w2 = ws[(int64_t)(i + 2) * C + c], w3 = ws[(int64_t)(i + 3) * C + c];
+            const float h0 = h[(int64_t)i * ld_h + k], h1 = h[(int64_t)(i + 1) * ld_h + k];
+            const float h2 = h[(int64_t)(i + 2) * ld_h + k], h3 = h[(int64_t)(i + 3) * ld_h + k];
+            acc = fmaf(w0, h0, acc); acc = fmaf(w1, h1, acc); acc = fmaf(w2, h2, acc); acc = fmaf(w3, h3, acc);
+        }
+        for (; i < i1; ++i) acc = fmaf(ws[(int64_t)i * C + c], h[(int64_t)i * ld_h + k], acc);
+        part[((int64_t)z * C + c) * d + k] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(256)
-xent_wgrad_kernel(const float* __restrict__ h, int64_t ld_h, int d, int C, int n,
-                  const float* __restrict__ ws, float* __restrict__ gwc, int64_t ld_gwc, float* __restrict__ loss) {
-    const int c = blockIdx.x;
+xent_finish_kernel(const float* __restrict__ part, const float* __restrict__ ws, int d, int C, int n,
+                   float* __restrict__ gwc, int64_t ld_gwc, float* __restrict__ loss) {
     if (gwc != nullptr) {
-        for (int k = threadIdx.x; k < d; k += blockDim.x) {
-            float acc = 0.f;
-            for (int i = 0; i < n; ++i) acc = fmaf(ws[(int64_t)i * C + c], h[(int64_t)i * ld_h + k], acc);
-            gwc[(int64_t)c * ld_gwc + k] = acc;
+        const int e = blockIdx.x * blockDim.x + threadIdx.x;
+        if (e < C * d) {
+            float s = 0.f;
+#pragma unroll
+            for (int z = 0; z < kWgradSplits; ++z) s += part[(int64_t)z * C * d + e];
+            const int c = e / d, k = e - c * d;
+            gwc[(int64_t)c * ld_gwc + k] = s;
         }
     }
-    if (c == 0 && loss != nullptr) {
-        __shared__ float part[256];
+    if (blockIdx.x == 0 && loss != nullptr) {
+        __shared__ float red[256];
         float s = 0.f;
         for (int i = threadIdx.x; i < n; i += blockDim.x) s += ws[(int64_t)n * C + i];
-        part[threadIdx.x] = s;
+        red[threadIdx.x] = s;
         __syncthreads();
         for (int o = 128; o; o >>= 1) {
-            if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
             __syncthreads();
         }
-        if (threadIdx.x == 0) loss[0] = part[0] / (float)n;
+        if (threadIdx.x == 0) loss[0] = red[0] / (float)n;
     }
 }
 
 }  // namespace
+
+extern "C" int64_t gs_classifier_ws_floats(int32_t n, int32_t d, int32_t num_classes) {
+    return (int64_t)n * num_classes + n + (int64_t)kWgradSplits * num_classes * d;
+}
 
 extern "C" int gs_classifier_xent(const float* h, int64_t ld_h, const float* wc, int64_t ld_wc,
                                   const int64_t* labels, int32_t d, int32_t num_classes, int32_t n,
@@ -130,7 +159,12 @@ extern "C" int gs_classifier_xent(const float* h, int64_t ld_h, const float* wc,
     xent_rows_kernel<<<(n + kRowsPerBlock - 1) / kRowsPerBlock, kRowsPerBlock * 32, smem, s>>>(
         h, ld_h, wc, ld_wc, labels, d, num_classes, n, grad_scale / (float)n, logits, ld_logits, gh, ld_gh, ws);
     GS_LAUNCH_CHECK();
-    xent_wgrad_kernel<<<num_classes, 256, 0, s>>>(h, ld_h, d, num_classes, n, ws, gwc, ld_gwc, loss);
+    float* part = ws + (int64_t)n * num_classes + n;
+    if (gwc != nullptr) {
+        xent_wgrad_partial_kernel<<<dim3(num_classes, kWgradSplits), 128, 0, s>>>(h, ld_h, d, num_classes, n, ws, part);
+        GS_LAUNCH_CHECK();
+    }
+    xent_finish_kernel<<<(num_classes * d + 255) / 256, 256, 0, s>>>(part, ws, d, num_classes, n, gwc, ld_gwc, loss);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }

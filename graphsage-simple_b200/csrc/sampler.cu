@@ -88,6 +88,73 @@ sample_csr_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
     cnt[i] = c;
 }
 
+// Warp-per-row variant for k <= 32 (the common fan-outs): every lane draws its own Philox word
+// up front, Floyd's sequential membership test is one ballot per draw, the ascending order
+// comes from a rank count over shuffles, and the CSR reads/tile writes are coalesced.  Same
+// specification (and bit-identical output) as the thread-per-row kernel above.
+constexpr int kWarpRows = 8;      // warps (rows) per block
+
+__global__ void __launch_bounds__(kWarpRows * 32)
+sample_csr_warp_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                       const int32_t* __restrict__ nodes, int n_max, const int32_t* __restrict__ n_dev,
+                       int k, int width, int add_self, uint32_t seed_lo, uint32_t seed_hi,
+                       int64_t step_imm, const int64_t* __restrict__ step_dev,
+                       uint32_t tag_head, uint32_t tag_tail, int n_head,
+                       int32_t* __restrict__ idx, int32_t* __restrict__ cnt) {
+    const int n = gs_row_count(n_max, n_dev);
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kWarpRows + (threadIdx.x >> 5);
+    if (i >= n_max) return;
+    int32_t* out = idx + (int64_t)i * width;
+    if (i >= n) {
+        for (int j = lane; j < width; j += 32) out[j] = -1;
+        if (lane == 0) cnt[i] = 0;
+        return;
+    }
+    const int32_t v = nodes[i];
+    const int64_t base = rowptr[v];
+    const int deg = (int)(rowptr[v + 1] - base);
+    int c;
+    bool has_self = false;
+    if (k < 0 || deg <= k) {
+        c = deg < width ? deg : width;
+        for (int j = lane; j < c; j += 32) {
+            const int32_t u = col[base + j];
+            has_self |= (u == v);
+            out[j] = u;
+        }
+    } else {
+        const uint32_t step = (uint32_t)(step_dev ? *step_dev : step_imm);
+        const uint32_t tag = i < n_head ? tag_head : tag_tail;
+        uint32_t r = 0;
+        if (lane < k) r = philox4x32_10((uint32_t)v, (uint32_t)(lane >> 2), step, tag, seed_lo, seed_hi).c[lane & 3];
+        int mine = -1;                               // lane m holds the m-th chosen position
+        for (int m = 0; m < k; ++m) {
+            const int j = deg - k + m;
+            const uint32_t rm = __shfl_sync(0xffffffffu, r, m);
+            int t = (int)(((uint64_t)rm * (uint64_t)(j + 1)) >> 32);
+            const unsigned dup = __ballot_sync(0xffffffffu, lane < m && mine == t);
+            if (dup) t = j;
+            if (lane == m) mine = t;
+        }
+        int rank = 0;
+        for (int l = 0; l < k; ++l) rank += (__shfl_sync(0xffffffffu, mine, l) < mine) ? 1 : 0;
+        if (lane < k) {
+            const int32_t u = col[base + mine];
+            has_self = (u == v);
+            out[rank] = u;
+        }
+        c = k;
+    }
+    has_self = __any_sync(0xffffffffu, has_self);
+    if (add_self && !has_self && c < width) {
+        if (lane == 0) out[c] = v;
+        ++c;
+    }
+    for (int j = c + lane; j < width; j += 32) out[j] = -1;
+    if (lane == 0) cnt[i] = c;
+}
+
 // ---- dedup: mark -> count(+scan of block sums by the last block) -> compact -> remap ----
 constexpr int kChunk = 2048;       // node ids per block in the count/compact passes
 constexpr int kScanThreads = 256;
@@ -224,10 +291,16 @@ extern "C" int gs_sample_csr(const int64_t* rowptr, const int32_t* col, int32_t 
     if (k > kMaxK) return GS_ENOSUP;
     if (k >= 0 && width < k + (add_self ? 1 : 0)) return GS_EINVAL;
     if (n_max == 0) return GS_OK;
-    const int threads = 128;
-    sample_csr_kernel<<<(n_max + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
-        rowptr, col, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed, (uint32_t)(seed >> 32),
-        step, step_dev, tag_head, tag_tail, n_head, idx, cnt);
+    if (k <= 32) {
+        sample_csr_warp_kernel<<<(n_max + kWarpRows - 1) / kWarpRows, kWarpRows * 32, 0, (cudaStream_t)stream>>>(
+            rowptr, col, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed, (uint32_t)(seed >> 32),
+            step, step_dev, tag_head, tag_tail, n_head, idx, cnt);
+    } else {
+        const int threads = 128;
+        sample_csr_kernel<<<(n_max + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+            rowptr, col, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed, (uint32_t)(seed >> 32),
+            step, step_dev, tag_head, tag_tail, n_head, idx, cnt);
+    }
     GS_LAUNCH_CHECK();
     return GS_OK;
 }

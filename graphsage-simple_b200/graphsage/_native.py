@@ -35,6 +35,7 @@ SIGNATURES = {
     "gs_encoder_wgrad_tc_ws_floats": (_i64, [_i32, _i32, _i32]),
     "gs_encoder_wgrad_tc": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr,
                                    _ptr, _i64, _ptr, _ptr]),
+    "gs_classifier_ws_floats": (_i64, [_i32, _i32, _i32]),
     "gs_classifier_xent": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i32, _i32, _i32, _f32, _ptr, _i64, _ptr,
                                   _ptr, _i64, _ptr, _i64, _ptr, _ptr]),
     "gs_sgd_step": (_i32, [_ptr, _ptr, _f32, _i64, _ptr]),

@@ -81,7 +81,7 @@ class TrainEngine:
         ws = max(ops.encoder_bwd_ws_floats(n1_max, self.K1, self.d1),
                  ops.encoder_bwd_ws_floats(B, self.K2, self.d2), 4)
         self.ws = torch.empty(ws, device=dev)
-        self.xent_ws = torch.empty(B * self.C + B, device=dev)
+        self.xent_ws = torch.empty(ops.classifier_ws_floats(B, self.d2, self.C), device=dev)
         # layer 1 runs on the tcgen05 path when the shape qualifies (d1 == 128, K1 % 4 == 0)
         self.tc1 = ops.encoder_tc_supported(self.K1, self.d1)
         if self.tc1:

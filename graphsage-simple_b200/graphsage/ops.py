@@ -203,19 +203,23 @@ def encoder_wgrad_tc(x, h, gh, act, gw, ws=None, n_dev=None):
     return gw
 
 
+def classifier_ws_floats(n, d, c):
+    return int(N.load().gs_classifier_ws_floats(int(n), int(d), int(c)))
+
+
 def classifier_xent(h, wc, labels, grad_scale=1.0, logits=None, loss=None, gh=None, gwc=None, ws=None):
     lib = N.load()
     N.require_cuda(h, wc, labels)
     n, d = h.shape
     c = wc.shape[0]
     if ws is None:
-        ws = torch.empty(n * c + n, device=h.device, dtype=torch.float32)
+        ws = torch.empty(classifier_ws_floats(n, d, c), device=h.device, dtype=torch.float32)
     N.check(lib.gs_classifier_xent(N.ptr(h), h.stride(0), N.ptr(wc), wc.stride(0), N.ptr(labels), d, c, n,
                                    float(grad_scale), N.ptr(logits), logits.stride(0) if logits is not None else 0,
                                    N.ptr(loss), N.ptr(gh), gh.stride(0) if gh is not None else 0,
                                    N.ptr(gwc), gwc.stride(0) if gwc is not None else 0, N.ptr(ws), N.stream()),
             "gs_classifier_xent")
-    LAUNCHES[0] += 2
+    LAUNCHES[0] += 3 if gwc is not None else 2
     return loss
 
 

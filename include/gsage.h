@@ -146,7 +146,8 @@ GS_API int gs_encoder_wgrad_tc(const float* x, int64_t ld_x, const float* h, int
  *   loss[0]      = mean_i ( logsumexp(logits[i]) - logits[i, labels[i]] )
  *   gh[i, :]     = grad_scale/n * (softmax(logits[i]) - onehot) . wc      (if gh  != NULL)
  *   gwc[c, :]    = grad_scale/n * sum_i (softmax - onehot)[i,c] * h[i,:]  (if gwc != NULL)
- * ws must hold n * num_classes + n floats.                                                */
+ * ws must hold gs_classifier_ws_floats(n, d, num_classes) floats.                          */
+GS_API int64_t gs_classifier_ws_floats(int32_t n, int32_t d, int32_t num_classes);
 GS_API int gs_classifier_xent(const float* h, int64_t ld_h, const float* wc, int64_t ld_wc,
                        const int64_t* labels, int32_t d, int32_t num_classes, int32_t n,
                        float grad_scale, float* logits, int64_t ld_logits, float* loss,
