@@ -2,6 +2,7 @@
 // Replaces graphsage/aggregators.py:54-65,74 (dense mask + mask.mm), encoders.py:49-54
 // (self lookup + cat), the autograd backward of mask.mm (model.py:249) and the SGD step
 // (model.py:250) of the reference.
+#include <cstdlib>
 #include "gs_common.cuh"
 
 namespace {
@@ -41,16 +42,17 @@ __device__ __forceinline__ void store_chunk(float* __restrict__ dst_row, int c4,
 // CH chunks per lane are kept in registers and NB neighbours are in flight at once, i.e.
 // CH*NB independent 128-bit loads per lane, which is what hides HBM latency here.
 template <int CH, int NB>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
 gather_mean_kernel(const float* __restrict__ table, int64_t ld_table, int dim,
                    const int32_t* __restrict__ idx, const int32_t* __restrict__ cnt, int width,
                    const int32_t* __restrict__ self_ids, int n_max, const int32_t* __restrict__ n_dev,
                    float* __restrict__ out, int64_t ld_out, int neigh_off, int out_align) {
     const int n = gs_row_count(n_max, n_dev);
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (row >= n) return;
     const int nchunks = (dim + 3) >> 2;
+    // grid-stride over rows: the grid is capped at a fixed number of blocks per SM so that the
+    // kernel leaves room for a co-resident tensor-core CTA (engine.py pipelining)
+    for (int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < n; row += gridDim.x * kWarpsPerBlock) {
     const int c = min(cnt[row], width);
     const float inv = c > 0 ? 1.f / (float)c : 0.f;
     float* orow = out + (int64_t)row * ld_out;
@@ -107,6 +109,7 @@ gather_mean_kernel(const float* __restrict__ table, int64_t ld_table, int dim,
                 store_chunk(orow + neigh_off, c4, dim, out_align, m);
             }
         }
+    }
     }
 }
 
@@ -189,7 +192,15 @@ extern "C" int gs_gather_mean_fwd(const float* table, int64_t ld_table, int32_t 
     if (n_max == 0) return GS_OK;
     const int align = (neigh_off & 3) == 0 ? 4 : ((neigh_off & 1) == 0 ? 2 : 1);
     const int nchunks = (dim + 3) / 4;
-    const dim3 grid((n_max + kWarpsPerBlock - 1) / kWarpsPerBlock), block(kWarpsPerBlock * 32);
+    static int bps = 0;                 // blocks per SM cap (GSAGE_GATHER_BPS, default 2: leaves room for a co-resident tcgen05 CTA)
+    if (bps == 0) {
+        const char* e = getenv("GSAGE_GATHER_BPS");
+        bps = e ? atoi(e) : 2;
+        if (bps < 1) bps = 1;
+    }
+    int nblocks = (n_max + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (nblocks > GS_NUM_SMS * bps) nblocks = GS_NUM_SMS * bps;
+    const dim3 grid(nblocks), block(kWarpsPerBlock * 32);
     cudaStream_t s = (cudaStream_t)stream;
 #define GS_GM(CH, NB) gather_mean_kernel<CH, NB><<<grid, block, 0, s>>>(table, ld_table, dim, idx, cnt, width, \
         self_ids, n_max, n_dev, out, ld_out, neigh_off, align)

@@ -24,6 +24,29 @@ from . import ops, sampling
 _SIGMOID = ("node_degree", "shared", "pagerank")
 
 
+class _FrontierSet:
+    """Everything one minibatch's sample -> gather chain produces, plus its staged inputs.  Two
+    sets exist so that the chain for batch t+1 can run while batch t is in its GEMM/backward
+    chain (``TrainEngine.train_step_pipelined``)."""
+
+    def __init__(self, eng):
+        dev, B, n1_max = eng.dev, eng.B, eng.n1_max
+        i32 = dict(device=dev, dtype=torch.int32)
+        # per-step inputs: one pinned staging block [step | labels | targets] -> one H2D copy
+        self.stage_host = torch.empty(8 + 8 * B + 4 * B, dtype=torch.uint8).pin_memory()
+        self.stage_dev = torch.zeros(8 + 8 * B + 4 * B, dtype=torch.uint8, device=dev)
+        self.step_dev = self.stage_dev[:8].view(torch.int64)
+        self.labels = self.stage_dev[8:8 + 8 * B].view(torch.int64)
+        self.targets = self.stage_dev[8 + 8 * B:].view(torch.int32)
+        self.idx2 = torch.empty((B, eng.w2_width), **i32)
+        self.cnt2 = torch.empty(B, **i32)
+        self.frontier1 = torch.zeros(n1_max, **i32)
+        self.n1_dev = torch.zeros(1, **i32)
+        self.idx1 = torch.empty((n1_max, eng.w1_width), **i32)
+        self.cnt1 = torch.empty(n1_max, **i32)
+        self.comb1 = ops.empty_rows(n1_max, eng.K1, dev, zero=True)
+
+
 class TrainEngine:
     def __init__(self, graph1, graph2, table, feat_dim, d1, d2, num_classes, k1, k2, max_batch,
                  gcn=False, agg_gcn1=False, agg_gcn2=False, act1=ops.ACT_RELU, act2=ops.ACT_RELU,
@@ -48,25 +71,12 @@ class TrainEngine:
         self.n1_max = n1_max
         self.K1 = self.F if self.gcn else 2 * self.F
         self.K2 = self.d1 if self.gcn else 2 * self.d1
-        i32 = dict(device=dev, dtype=torch.int32)
-        # per-step inputs: one pinned staging block [step | labels | targets] -> one H2D copy
-        self.stage_host = torch.empty(8 + 8 * B + 4 * B, dtype=torch.uint8).pin_memory()
-        self.stage_dev = torch.empty(8 + 8 * B + 4 * B, dtype=torch.uint8, device=dev)
-        self.step_dev = self.stage_dev[:8].view(torch.int64)
-        self.labels = self.stage_dev[8:8 + 8 * B].view(torch.int64)
-        self.targets = self.stage_dev[8 + 8 * B:].view(torch.int32)
+        self.sets = [_FrontierSet(self)]           # the second set is created on first pipelined use
+        self.cur = 0
         self.loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
-        # sampled structure
-        self.idx2 = torch.empty((B, self.w2_width), **i32)
-        self.cnt2 = torch.empty(B, **i32)
-        self.frontier1 = torch.zeros(n1_max, **i32)
-        self.n1_dev = torch.zeros(1, **i32)
-        self.idx1 = torch.empty((n1_max, self.w1_width), **i32)
-        self.cnt1 = torch.empty(n1_max, **i32)
-        self.self2 = torch.arange(B, **i32)
+        self.self2 = torch.arange(B, device=dev, dtype=torch.int32)
         self.scratch = ops.DedupScratch(graph2.num_nodes, dev)
         # activations (row-major, ld % 4 == 0)
-        self.comb1 = ops.empty_rows(n1_max, self.K1, dev, zero=True)
         self.h1 = ops.empty_rows(n1_max, self.d1, dev, zero=True)
         self.comb2 = ops.empty_rows(B, self.K2, dev, zero=True)
         self.h2 = ops.empty_rows(B, self.d2, dev, zero=True)
@@ -102,39 +112,62 @@ class TrainEngine:
         self._graphs = {}
         self._warm = set()
         self._launch_count = {}
+        self._side = None
+
+    # convenience views of the current frontier set (tests / bench read these)
+    @property
+    def n1_dev(self):
+        return self.sets[self.cur].n1_dev
+
+    @property
+    def cnt1(self):
+        return self.sets[self.cur].cnt1
+
+    @property
+    def cnt2(self):
+        return self.sets[self.cur].cnt2
 
     # ------------------------------------------------------------------ the launch sequence
-    def _forward_backward(self, b):
-        """Enqueue one fwd+bwd over the first ``b`` staged targets on the current stream."""
+    def _n1_max(self, b):
+        return min(b * self.w2_width, self.g2.num_nodes) + self.slot_base_of(b)
+
+    def _gather_chain(self, fs, b):
+        """sample -> dedup -> sample -> gather for the ``b`` staged targets of frontier set ``fs``:
+        everything of a step that does not depend on the weights."""
         seed = sampling.get_seed()
         base = self.slot_base_of(b)
-        targets, labels = self.targets[:b], self.labels[:b]
-        idx2, cnt2 = self.idx2[:b], self.cnt2[:b]
-        n = 0
+        targets = fs.targets[:b]
+        idx2, cnt2 = fs.idx2[:b], fs.cnt2[:b]
         # layer-2 tile over the targets (aggregators.py:42-48; RNG draw of agg2)
         ops.sample_csr(self.g2.rowptr, self.g2.col, self.g2.num_nodes, targets, self.k2, add_self=self.agg_gcn2,
-                       seed=seed, step_dev=self.step_dev, tag_head=sampling.call_tag(self.uid2, 0),
+                       seed=seed, step_dev=fs.step_dev, tag_head=sampling.call_tag(self.uid2, 0),
                        width=self.w2_width, idx=idx2, cnt=cnt2)
         # frontier of layer 1: [targets (SAGE self pass) | distinct hop-1 ids] (aggregators.py:52-56)
         if not self.gcn:
-            self.frontier1[:b].copy_(targets)
-        ops.dedup_remap(idx2, cnt2, self.scratch, slot_base=base, uniq=self.frontier1[base:], n_total=self.n1_dev)
-        n1_max = min(b * self.w2_width, self.g2.num_nodes) + base
-        fr = self.frontier1[:n1_max]
-        idx1, cnt1 = self.idx1[:n1_max], self.cnt1[:n1_max]
+            fs.frontier1[:b].copy_(targets)
+        ops.dedup_remap(idx2, cnt2, self.scratch, slot_base=base, uniq=fs.frontier1[base:], n_total=fs.n1_dev)
+        n1_max = self._n1_max(b)
+        fr = fs.frontier1[:n1_max]
+        idx1, cnt1 = fs.idx1[:n1_max], fs.cnt1[:n1_max]
         # layer-1 tiles: rows < b are the self pass over the batch nodes (independent draw,
         # call index 1), the rest the hop-1 pass (call index 0)  -- SURVEY.md s3.2
         ops.sample_csr(self.g1.rowptr, self.g1.col, self.g1.num_nodes, fr, self.k1, add_self=self.agg_gcn1,
-                       seed=seed, step_dev=self.step_dev, tag_head=sampling.call_tag(self.uid1, 1),
-                       tag_tail=sampling.call_tag(self.uid1, 0), n_head=base, n_dev=self.n1_dev,
+                       seed=seed, step_dev=fs.step_dev, tag_head=sampling.call_tag(self.uid1, 1),
+                       tag_tail=sampling.call_tag(self.uid1, 0), n_head=base, n_dev=fs.n1_dev,
                        width=self.w1_width, idx=idx1, cnt=cnt1)
-        comb1, h1 = self.comb1[:n1_max], self.h1[:n1_max]
-        ops.gather_mean_fwd(self.table, self.F, idx1, cnt1, comb1, neigh_off=0 if self.gcn else self.F,
-                            self_ids=None if self.gcn else fr, n_dev=self.n1_dev)
+        ops.gather_mean_fwd(self.table, self.F, idx1, cnt1, fs.comb1[:n1_max], neigh_off=0 if self.gcn else self.F,
+                            self_ids=None if self.gcn else fr, n_dev=fs.n1_dev)
+
+    def _compute_chain(self, fs, b):
+        """Encoder GEMMs, classifier/loss and the whole backward for frontier set ``fs``."""
+        n1_max = self._n1_max(b)
+        labels = fs.labels[:b]
+        idx2, cnt2 = fs.idx2[:b], fs.cnt2[:b]
+        comb1, h1 = fs.comb1[:n1_max], self.h1[:n1_max]
         if self.tc1:
-            ops.encoder_fwd_tc(comb1, self.w1, self.act1, h1, ws=self.tc_ws, n_dev=self.n1_dev)
+            ops.encoder_fwd_tc(comb1, self.w1, self.act1, h1, ws=self.tc_ws, n_dev=fs.n1_dev)
         else:
-            ops.encoder_fwd(comb1, self.w1, self.act1, h1, n_dev=self.n1_dev)
+            ops.encoder_fwd(comb1, self.w1, self.act1, h1, n_dev=fs.n1_dev)
         comb2, h2 = self.comb2[:b], self.h2[:b]
         ops.gather_mean_fwd(self.h1, self.d1, idx2, cnt2, comb2, neigh_off=0 if self.gcn else self.d1,
                             self_ids=None if self.gcn else self.self2[:b])
@@ -148,15 +181,31 @@ class TrainEngine:
         ops.scatter_mean_bwd(self.gcomb2[:b], self.d1, idx2, cnt2, self.gh1, neigh_off=0 if self.gcn else self.d1,
                              self_ids=None if self.gcn else self.self2[:b])
         if self.tc1:
-            ops.encoder_wgrad_tc(comb1, h1, gh1, self.act1, self.gw1, ws=self.tc_ws, n_dev=self.n1_dev)
+            ops.encoder_wgrad_tc(comb1, h1, gh1, self.act1, self.gw1, ws=self.tc_ws, n_dev=fs.n1_dev)
         else:
             ops.encoder_bwd(comb1, self.w1, h1, gh1, self.act1, self.gw1, None, dz=self.dz1, ws=self.ws,
-                            n_dev=self.n1_dev)
-        return n
+                            n_dev=fs.n1_dev)
+
+    def _forward_backward(self, b):
+        """Enqueue one fwd+bwd over the first ``b`` staged targets on the current stream."""
+        fs = self.sets[self.cur]
+        self._gather_chain(fs, b)
+        self._compute_chain(fs, b)
 
     def _update(self, lr):
         ops.sgd_step(self.flat_w, self.flat_g, lr)
-        ops.advance_step(self.step_dev)
+
+    def _overlapped(self, parity, b, b_next, lr):
+        """compute chain of set[parity] on the current stream || gather chain of set[1-parity] on a
+        side stream (fork/join, so the pair is one CUDA graph); lr=None leaves SGD to the caller."""
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self._gather_chain(self.sets[1 - parity], b_next)
+        self._compute_chain(self.sets[parity], b)
+        if lr is not None:
+            self._update(lr)
+        main.wait_stream(self._side)
 
     # ------------------------------------------------------------------ graph capture / replay
     def _run(self, key, fn):
@@ -182,17 +231,20 @@ class TrainEngine:
     def launches_per_step(self):
         """Kernels of libgsage_sm100.so in one train step (fwd+bwd+SGD), counted when enqueued."""
         c = self._launch_count
-        whole = [v for k, v in c.items() if k[0] == "step"]
+        whole = [v for k, v in c.items() if k[0] in ("step", "pipe")]
         if whole:
             return max(whole)
-        return max([v for k, v in c.items() if k[0] == "fb"] or [0]) + max([v for k, v in c.items() if k[0] == "sgd"] or [0])
+        return max([v for k, v in c.items() if k[0] in ("fb", "pipe_fb")] or [0]) + \
+            max([v for k, v in c.items() if k[0] == "sgd"] or [0])
 
-    def stage(self, nodes, labels, step):
-        """Host -> device copy of one minibatch's inputs (ids, labels, sampler step)."""
+    def stage(self, nodes, labels, step, slot=None):
+        """Host -> device copy of one minibatch's inputs (ids, labels, sampler step) into frontier
+        set ``slot`` (default: the current one)."""
         b = len(nodes)
         if b > self.B:
             raise ValueError("batch of %d exceeds the engine's max_batch %d" % (b, self.B))
-        h = self.stage_host
+        fs = self.sets[self.cur if slot is None else slot]
+        h = fs.stage_host
         h[:8].view(torch.int64)[0] = int(step)
         if isinstance(labels, torch.Tensor):
             h[8:8 + 8 * b].view(torch.int64).copy_(labels.reshape(-1))
@@ -203,11 +255,20 @@ class TrainEngine:
         else:
             h[8 + 8 * self.B:8 + 8 * self.B + 4 * b].view(torch.int32).copy_(
                 torch.from_numpy(np.asarray(nodes, dtype=np.int32)))
-        self.stage_dev.copy_(h, non_blocking=True)
+        fs.stage_dev.copy_(h, non_blocking=True)
+        return b
+
+    def stage_device(self, d_nodes, d_labels, step, slot=None):
+        """Same as ``stage`` for inputs that already live in HBM (device-to-device copies)."""
+        fs = self.sets[self.cur if slot is None else slot]
+        b = d_nodes.shape[0]
+        fs.targets[:b].copy_(d_nodes)
+        fs.labels[:b].copy_(d_labels)
+        fs.step_dev.fill_(int(step))
         return b
 
     def forward_backward(self, b):
-        self._run(("fb", b), lambda: self._forward_backward(b))
+        self._run(("fb", b, self.cur), lambda: self._forward_backward(b))
 
     def update(self, lr):
         self._run(("sgd", float(lr)), lambda: self._update(lr))
@@ -216,11 +277,37 @@ class TrainEngine:
         """fwd + bwd (+ gradient all-reduce) + SGD on the staged batch; returns nothing (the
         loss stays in ``self.loss`` on the device)."""
         if allreduce is None:
-            self._run(("step", b, float(lr)), lambda: (self._forward_backward(b), self._update(lr)))
+            self._run(("step", b, float(lr), self.cur), lambda: (self._forward_backward(b), self._update(lr)))
         else:
             self.forward_backward(b)
             allreduce(self.flat_g)
             self.update(lr)
+
+    # ---- software pipelining across minibatches ---------------------------------------------
+    def enable_pipeline(self):
+        if len(self.sets) == 1:
+            self.sets.append(_FrontierSet(self))
+            self._side = torch.cuda.Stream(device=self.dev)
+
+    def prime(self, b):
+        """Run the gather chain of the CURRENT set (first batch of a pipelined run)."""
+        self.enable_pipeline()
+        self._run(("prime", b, self.cur), lambda: self._gather_chain(self.sets[self.cur], b))
+
+    def train_step_pipelined(self, b, lr, b_next=None, allreduce=None):
+        """One train step on the current set (its gather chain already done by ``prime`` or by the
+        previous call) while the sample -> gather chain of the NEXT batch -- already staged in the
+        other set -- runs concurrently on a side stream.  Afterwards the sets swap roles."""
+        self.enable_pipeline()
+        b_next = b if b_next is None else b_next
+        p = self.cur
+        if allreduce is None:
+            self._run(("pipe", b, b_next, float(lr), p), lambda: self._overlapped(p, b, b_next, lr))
+        else:
+            self._run(("pipe_fb", b, b_next, p), lambda: self._overlapped(p, b, b_next, None))
+            allreduce(self.flat_g)
+            self.update(lr)
+        self.cur = 1 - p
 
     def read_loss(self):
         self.loss_host.copy_(self.loss, non_blocking=True)

@@ -52,15 +52,40 @@ class SupervisedGraphSage(nn.Module):
         embeds = self.enc(nodes)
         return SoftmaxXent.apply(embeds.t(), self.weight, self._labels(labels))
 
-    def train_step(self, nodes, labels, lr=0.7):
+    grad_allreduce = None   # data parallel: callable(flat_grads) run between backward and the SGD step
+
+    def train_step(self, nodes, labels, lr=0.7, prefetch=None):
         """The reference's timed unit (model.py:246-250: zero_grad, loss, backward, SGD step) as
-        one fused call; returns the loss as a Python float (one 4-byte device->host read)."""
+        one fused call; returns the loss as a Python float (one 4-byte device->host read).
+
+        ``prefetch=(next_nodes, next_labels)`` starts the NEXT minibatch's neighbour sampling and
+        feature gather on a side stream while this one is in its GEMM/backward chain (the
+        data-loader style overlap the reference's single Python thread cannot do); pass the same
+        batch as ``nodes, labels`` of the following call."""
         from .engine import engine_for
         from . import sampling
-        eng = engine_for(self, len(nodes))
+        eng = engine_for(self, max(len(nodes), len(prefetch[0]) if prefetch is not None else 0))
         if eng is None:
             raise RuntimeError("train_step needs the canonical 2-layer wiring (model.py:214-227)")
         with sampling.top_level_call() as step:
-            b = eng.stage(nodes, labels, step)
-            eng.train_step(b, lr)
+            if prefetch is None and getattr(self, "_primed", None) is None:
+                b = eng.stage(nodes, labels, step)
+                eng.train_step(b, lr, self.grad_allreduce)
+                return eng.read_loss()
+            primed = getattr(self, "_primed", None)
+            if primed is None or len(primed) != len(nodes) or not np.array_equal(primed, np.asarray(nodes)):
+                b = eng.stage(nodes, labels, step)          # not prefetched: do its gather chain now
+                eng.prime(b)
+            b = len(nodes)
+            if prefetch is not None:
+                eng.enable_pipeline()
+                nb = eng.stage(prefetch[0], prefetch[1], step + 1, slot=1 - eng.cur)
+                eng.train_step_pipelined(b, lr, nb, self.grad_allreduce)
+                self._primed = np.array(prefetch[0], copy=True)
+            else:                                           # last batch of a pipelined run
+                eng._run(("tail", b, eng.cur), lambda: eng._compute_chain(eng.sets[eng.cur], b))
+                if self.grad_allreduce is not None:
+                    self.grad_allreduce(eng.flat_g)
+                eng.update(lr)
+                self._primed = None
         return eng.read_loss()

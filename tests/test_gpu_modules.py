@@ -267,3 +267,33 @@ def test_fused_train_step_matches_reference_replay(golden):
         assert relerr(model.weight.detach().cpu().numpy(), g["wc_new"]) < REL
         assert relerr(enc2.weight.detach().cpu().numpy(), g["w2_new"]) < REL
         assert relerr(enc1.weight.detach().cpu().numpy(), g["w1_new"]) < REL
+
+
+@pytest.mark.parametrize("gcn", [False, True])
+def test_pipelined_prefetch_equals_sequential_steps(golden, gcn):
+    """train_step(..., prefetch=next batch) overlaps the next batch's sample->gather chain with
+    this batch's compute chain; losses and weights must equal the plain sequential steps."""
+    from graphsage import sampling
+    g = golden("model_live")
+    tag = "gcn" if gcn else "sage"
+    gg = dict(g, w1=g[tag + "_w1"], w2=g[tag + "_w2"], wc=g[tag + "_wc"])
+    adj = csr_to_adj(g["rowptr"], g["col"])
+    k1, k2 = int(g["k1"]), int(g["k2"])
+    rng = np.random.default_rng(3)
+    n = len(g["rowptr"]) - 1
+    batches = [rng.permutation(n)[:32] for _ in range(7)]
+    labels = [g["labels"][b] for b in batches]
+    out = {}
+    for mode in ("seq", "pipe"):
+        model, enc1, enc2 = build_model(gg, gcn, adj, adj, k1, k2)
+        sampling.seed(5)
+        losses = []
+        for i, b in enumerate(batches):
+            nxt = (batches[i + 1], labels[i + 1]) if (mode == "pipe" and i + 1 < len(batches)) else None
+            losses.append(model.train_step(b, labels[i], lr=0.1, prefetch=nxt))
+        out[mode] = (losses, [p.detach().cpu().numpy().copy() for p in (model.weight, enc2.weight, enc1.weight)])
+    for a, b in zip(out["seq"][0], out["pipe"][0]):
+        assert abs(a - b) / abs(a) < REL
+    for a, b in zip(out["seq"][1], out["pipe"][1]):
+        assert relerr(b, a) < REL
+    assert out["seq"][0][0] != out["seq"][0][-1]
