@@ -400,7 +400,7 @@ def profile_kernels(eng, B, lr, d_nodes, d_labels, iters=5):
         setattr(ops, name, timed)
 
     for nm in ("sample_csr", "dedup_remap", "gather_mean_fwd", "encoder_fwd", "encoder_fwd_tc", "classifier_xent",
-               "encoder_bwd", "encoder_wgrad_tc", "scatter_mean_bwd", "sgd_step"):
+               "encoder_bwd", "encoder_wgrad_tc", "encoder_dgrad", "scatter_mean_bwd", "sgd_step"):
         wrap(nm)
     try:
         for it in range(iters + 1):

@@ -5,22 +5,34 @@
 
 namespace {
 
-constexpr int kRowsPerBlock = 8;      // one warp per target row
+constexpr int kRowsPerBlock = 16;     // one warp per target row
 constexpr int kMaxClsPerLane = 4;     // num_classes <= 128
 
 // ws layout: dl[n, C] (scaled softmax - onehot), then loss_i[n]
+// One warp per target row, 16 rows per block.  The classifier weight is staged once per block in
+// shared memory with row stride d+1 (conflict-free when each lane walks its own class row).
 __global__ void __launch_bounds__(kRowsPerBlock * 32)
 xent_rows_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restrict__ wc, int64_t ld_wc,
                  const int64_t* __restrict__ labels, int d, int C, int n, float gscale,
                  float* __restrict__ logits, int64_t ld_logits, float* __restrict__ gh, int64_t ld_gh,
                  float* __restrict__ ws) {
     extern __shared__ float smem[];
-    float* s_wc = smem;                               // [C][d+1]  (stride d+1: conflict-free per-class reads)
+    float* s_wc = smem;                               // [C][d+1]
     float* s_h = smem + (size_t)C * (d + 1);          // [rows][d]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int e = threadIdx.x; e < C * d; e += blockDim.x) {
-        const int c = e / d, k = e - c * d;
-        s_wc[c * (d + 1) + k] = wc[(int64_t)c * ld_wc + k];
+    if ((d & 3) == 0 && (ld_wc & 3) == 0) {           // 128-bit global reads of the weight
+        const int d4 = d >> 2;
+        for (int e = threadIdx.x; e < C * d4; e += blockDim.x) {
+            const int c = e / d4, k = (e - c * d4) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(wc + (int64_t)c * ld_wc + k);
+            float* dst = s_wc + c * (d + 1) + k;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+    } else {
+        for (int e = threadIdx.x; e < C * d; e += blockDim.x) {
+            const int c = e / d, k = e - c * d;
+            s_wc[c * (d + 1) + k] = wc[(int64_t)c * ld_wc + k];
+        }
     }
     const int row = blockIdx.x * kRowsPerBlock + w;
     float* hrow = s_h + w * d;
@@ -34,10 +46,18 @@ xent_rows_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restr
 #pragma unroll
     for (int q = 0; q < kMaxClsPerLane; ++q) {
         const int c = lane + 32 * q;
-        float acc = 0.f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;          // 4 independent chains
         if (c < C) {
             const float* wr = s_wc + c * (d + 1);
-            for (int k = 0; k < d; ++k) acc = fmaf(hrow[k], wr[k], acc);
+            int k = 0;
+            for (; k + 4 <= d; k += 4) {
+                a0 = fmaf(hrow[k], wr[k], a0); a1 = fmaf(hrow[k + 1], wr[k + 1], a1);
+                a2 = fmaf(hrow[k + 2], wr[k + 2], a2); a3 = fmaf(hrow[k + 3], wr[k + 3], a3);
+            }
+            for (; k < d; ++k) a0 = fmaf(hrow[k], wr[k], a0);
+        }
+        const float acc = (a0 + a1) + (a2 + a3);
+        if (c < C) {
             zmax = fmaxf(zmax, acc);
             if (logits) logits[(int64_t)row * ld_logits + c] = acc;
         }
@@ -53,8 +73,9 @@ xent_rows_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restr
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float lse = zmax + logf(sum);
     const int y = (int)labels[row];
-    float dl[kMaxClsPerLane];
     float picked = 0.f;
+    float* s_dl = hrow;                               // the row's h is no longer needed below? (it is: keep separate)
+    float dl[kMaxClsPerLane];
 #pragma unroll
     for (int q = 0; q < kMaxClsPerLane; ++q) {
         const int c = lane + 32 * q;
@@ -66,20 +87,28 @@ xent_rows_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restr
             ws[(int64_t)row * C + c] = dl[q];
         }
     }
+    (void)s_dl;
 #pragma unroll
     for (int o = 16; o; o >>= 1) picked += __shfl_xor_sync(0xffffffffu, picked, o);
     if (lane == 0) ws[(int64_t)n * C + row] = lse - picked;
     if (gh != nullptr) {
-        for (int k = lane; k < d; k += 32) {
-            float acc = 0.f;
+        // gh[row, k] = sum_c dl[c] * wc[c, k]: lanes across k, classes broadcast by shuffle
+        for (int k0 = 0; k0 < d; k0 += 128) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int q = 0; q < kMaxClsPerLane; ++q)
-                for (int l = 0; l < 32; ++l) {
-                    const int c = l + 32 * q;
-                    if (c >= C) break;
-                    acc = fmaf(__shfl_sync(0xffffffffu, dl[q], l), s_wc[c * (d + 1) + k], acc);
+            for (int q = 0; q < kMaxClsPerLane; ++q) {
+                const int cmax = min(32, C - 32 * q);
+                for (int l = 0; l < cmax; ++l) {
+                    const float dv = __shfl_sync(0xffffffffu, dl[q], l);
+                    const float* wr = s_wc + (l + 32 * q) * (d + 1) + k0 + lane;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (k0 + lane + 32 * u < d) acc[u] = fmaf(dv, wr[32 * u], acc[u]);
                 }
-            gh[(int64_t)row * ld_gh + k] = acc;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k0 + lane + 32 * u < d) gh[(int64_t)row * ld_gh + k0 + lane + 32 * u] = acc[u];
         }
     }
 }

@@ -286,3 +286,22 @@ extern "C" int gs_encoder_bwd(const float* x, int64_t ld_x, const float* w, int6
     }
     return GS_OK;
 }
+
+// Input gradient only: gx[n, k_in] = (gh * act'(h)) . w   (used when the weight gradient runs on tcgen05)
+extern "C" int gs_encoder_dgrad(const float* w, int64_t ld_w, const float* h, int64_t ld_h,
+                                const float* gh, int64_t ld_gh, int32_t k_in, int32_t d_out, int32_t act,
+                                int32_t n_max, const int32_t* n_dev, float* dz, float* gx, int64_t ld_gx,
+                                void* stream) {
+    if (!w || !h || !gh || !dz || !gx || k_in <= 0 || d_out <= 0 || n_max < 0) return GS_EINVAL;
+    if (!gs_aligned16(w) || !gs_aligned16(dz) || !gs_aligned16(gx) || (ld_w & 3) || (ld_gx & 3)) return GS_EALIGN;
+    if (n_max == 0) return GS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int ld_dz = (d_out + 3) & ~3;
+    const int64_t total = (int64_t)n_max * d_out;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > GS_NUM_SMS * 8) blocks = GS_NUM_SMS * 8;
+    act_grad_kernel<<<(int)blocks, 256, 0, s>>>(h, ld_h, gh, ld_gh, d_out, act, n_max, n_dev, dz, ld_dz);
+    GS_LAUNCH_CHECK();
+    GemmArgs gd{dz, ld_dz, w, ld_w, gx, ld_gx, n_max, k_in, d_out, n_dev, 0, GS_ACT_NONE, ((d_out + BK - 1) / BK) * BK, 0};
+    return launch_gemm<false, true>(gd, 1, s);
+}

@@ -3,36 +3,47 @@
 // the encoder within the 1e-5 fp32 parity bar that a single TF32 pass misses.
 //
 //   forward  (NT):  H[n, 128]      = act( X[n, K] . W[128, K]^T )          X = combined tile
-//   backward (TN):  dW[128, K]     = dZ[n, 128]^T . X[n, K]                split over n
+//   backward (TN):  dW[128, K]^T   = X[n, K]^T . dZ[n, 128]                split over n
 //
 // Replaces `F.relu(self.weight.mm(combined.t()))` (graphsage/encoders.py:58-61) and the
 // MmBackward that produces `enc.weight.grad` (graphsage/model.py:249) of the reference.
 //
-// Structure per CTA (192 threads, 1 CTA/SM, 3-stage ring, 64 KB/stage):
-//   warp 0      TMA producer   X raw tile + pre-split Y_hi/Y_lo tiles -> smem (SWIZZLE_128B)
-//   warps 2..5  splitter       X raw -> X_hi (in place) + X_lo, elementwise so layout-agnostic;
-//                              later the epilogue (TMEM -> registers -> global)
-//   warp 1      MMA issuer     one elected lane: 4 k-steps x 3 tcgen05.mma per stage,
-//                              tcgen05.commit frees the stage / publishes the accumulator
+// In both kernels the A operand is derived from X (the combined tile, which needs the hi/lo
+// split and therefore has to pass through registers anyway) and is staged in TENSOR MEMORY:
+// the splitter warps read their row (NT) / column (TN) of the raw TMA tile from shared memory,
+// split it, and tcgen05.st the hi and lo halves into a TMEM slot; the MMA then takes A from
+// TMEM and only B -- the pre-split W or dZ tiles TMA wrote -- from shared memory.  That halves
+// the shared-memory read traffic of the MMAs, which (not the tensor pipe) bounded the first
+// version of this kernel (profiles/README.md, r01 tc_gemm v1 vs v2).
+//
+// Per CTA (192 threads, 1 CTA/SM): 4-stage smem ring of 48 KB (X raw, Y_hi, Y_lo), TMEM =
+// 2 main accumulators + 1 correction accumulator (3 x 128 columns) + 2 A slots (2 x 64 columns).
+//   warp 0      TMA producer
+//   warps 2..5  splitter (smem -> registers -> TMEM A slot), later the epilogue
+//   warp 1      MMA issuer (one lane): per stage 4 k-steps x 3 tcgen05.mma, tcgen05.commit
 #include <cuda.h>
+#include <cstdlib>
 #include "gs_common.cuh"
 
 namespace {
 
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 constexpr int kTile = 128;            // M and N of the UMMA tile (d_out == 128)
 constexpr int kChunk = 32;            // reduction elements per stage: 32 fp32 = one 128-B swizzle row
 constexpr int kOperandBytes = kTile * kChunk * 4;          // 16 KB
-constexpr int kStageBytes = 4 * kOperandBytes;             // X_hi, X_lo, Y_hi, Y_lo
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int kThreads = 192;
+constexpr int kStageBytes = 3 * kOperandBytes;             // X raw, Y_hi, Y_lo (pre-split in global memory)
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers + tmem slot*/;
+constexpr int kThreads = 320;          // TMA, MMA, 2 x 4 X-splitter/epilogue warps
 // The tensor core rounds toward zero when it adds a k-step into the fp32 accumulator: measured
 // bias ~1 ulp per tcgen05.mma (profiles/README.md), i.e. ~1e-5 relative after the 450 MMAs of a
 // K = 1204 row.  Spreading the hi.hi products over kMainAccs accumulators and keeping the two
 // 2^-11-sized correction products in their own accumulator cuts the number of roundings that
 // touch a large partial sum by 9x; the epilogue adds the accumulators in fp32 (round-to-nearest).
-constexpr int kMainAccs = 3;
-constexpr int kAccs = kMainAccs + 1;  // 4 x 128 columns = the SM's whole TMEM
+constexpr int kMainAccs = 2;
+constexpr int kAccs = kMainAccs + 1;  // 3 x 128 accumulator columns
+constexpr int kASlots = 2;            // TMEM staging slots for the A operand: 32 hi + 32 lo columns each
+constexpr int kASlotCols = 2 * kChunk;
+constexpr int kTmemCols = 512;        // 384 accumulator + 128 A-staging columns = the SM's whole TMEM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -59,6 +70,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -100,8 +114,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // Instruction descriptor: D fp32, A/B tf32, M = N = 128, dense.
-__host__ __device__ constexpr uint32_t make_idesc(bool mn_major) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((mn_major ? 1u : 0u) << 15) | ((mn_major ? 1u : 0u) << 16) |
+__host__ __device__ constexpr uint32_t make_idesc(bool b_mn_major) {
+    // A comes from tensor memory (row per lane, K along columns -> K-major); B is K-major (W) or N-major (dZ)
+    return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | ((b_mn_major ? 1u : 0u) << 16) |
            ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 }
 
@@ -121,7 +136,62 @@ struct TcArgs {
     int64_t ld_out;
     int rows_per_split;        // TN only (multiple of kChunk)
     int64_t split_stride;      // TN only
+    int debug;                 // experiment switches (GSAGE_TC_DEBUG), 0 in production
+    long long* trace;          // optional [64 chunks][16 events] clock64 trace of block 0 (GSAGE_TC_TRACE)
 };
+#define TC_TRACE(ev, c) do { if (g.trace && blockIdx.x == 0 && blockIdx.y == 0 && (c) < 64 && lane == 0) g.trace[(c) * 16 + (ev)] = clock64(); } while (0)
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t acc) {
+    // A from tensor memory, B from shared memory
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr),
+          "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// barrier slots (8 bytes each) after the stage ring
+constexpr int kBarFull = 0;                       // [kStages]  TMA bytes landed
+constexpr int kBarEmpty = kStages;                // [kStages]  stage's MMAs retired (tcgen05.commit)
+constexpr int kBarAReady = 2 * kStages;           // [kASlots]  splitter filled the TMEM A slot
+constexpr int kBarAFree = 2 * kStages + kASlots;  // [kASlots]  MMAs that read the slot retired
+constexpr int kBarAccum = 2 * kStages + 2 * kASlots;
+constexpr int kBarYReady = kBarAccum + 1;         // [kStages]  Y tile split into hi/lo in shared memory
 
 template <bool TN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -129,8 +199,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                const __grid_constant__ CUtensorMap map_ylo, TcArgs g) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = base + kStages * kStageBytes;        // full[3] ready[3] empty[3] accum
-    const uint32_t tmem_slot = bars + 128;
+    const uint32_t bars = base + kStages * kStageBytes;
+    const uint32_t tmem_slot = bars + 224;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -152,137 +222,179 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(bars + 8 * s, 1);                        // full: producer's expect_tx arrive
-            mbar_init(bars + 8 * (kStages + s), 4);            // ready: one arrive per splitter warp
-            mbar_init(bars + 8 * (2 * kStages + s), 1);        // empty: tcgen05.commit
+            mbar_init(bars + 8 * (kBarFull + s), 1);           // producer's expect_tx arrive
+            mbar_init(bars + 8 * (kBarEmpty + s), 1);          // tcgen05.commit
         }
-        mbar_init(bars + 8 * 3 * kStages, 1);                  // accumulator complete
+        for (int a = 0; a < kASlots; ++a) {
+            mbar_init(bars + 8 * (kBarAReady + a), 4);         // one arrive per warp of the slot's splitter group
+            mbar_init(bars + 8 * (kBarAFree + a), 1);          // tcgen05.commit
+        }
+        mbar_init(bars + 8 * kBarAccum, 1);
+        for (int st = 0; st < kStages; ++st) mbar_init(bars + 8 * (kBarYReady + st), 4);   // the chunk's 4 X-splitter warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {                                           // TMEM: 4 accumulators of 128 fp32 columns x 128 lanes
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kAccs * kTile));
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + kStages * kStageBytes + 128);
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + kStages * kStageBytes + 224);
+    const uint32_t tmem_a = tmem + kAccs * kTile;              // first A-staging column
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
         if (lane == 0) {
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % kStages, it = c / kStages;
-                mbar_wait(bars + 8 * (2 * kStages + s), (it & 1) ^ 1);
+                mbar_wait(bars + 8 * (kBarEmpty + s), (it & 1) ^ 1);
+                TC_TRACE(0, c);
                 const uint32_t st = base + s * kStageBytes;
-                const uint32_t full = bars + 8 * s;
-                mbar_expect_tx(full, 3 * kOperandBytes);
+                const uint32_t full = bars + 8 * (kBarFull + s);
                 const int kc = (chunk_begin + c) * kChunk;
+                if (g.debug & 8) { mbar_arrive(full); continue; }
+                mbar_expect_tx(full, 3 * kOperandBytes);
                 if (!TN) {
-                    tma_load_2d(st, &map_x, kc, x_fixed, full);                           // X rows, cols kc..
-                    tma_load_2d(st + 2 * kOperandBytes, &map_yhi, kc, 0, full);           // W_hi
-                    tma_load_2d(st + 3 * kOperandBytes, &map_ylo, kc, 0, full);           // W_lo
+                    tma_load_2d(st, &map_x, kc, x_fixed, full);                           // X rows (SW128)
+                    tma_load_2d(st + kOperandBytes, &map_yhi, kc, 0, full);               // W_hi (SW128, K-major)
+                    tma_load_2d(st + 2 * kOperandBytes, &map_ylo, kc, 0, full);           // W_lo
                 } else {
+                    tma_load_2d(st, &map_x, x_fixed, kc, full);                           // X [32 rows][128 cols], linear
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {                                         // 32-column blocks
-                        tma_load_2d(st + b * 4096, &map_x, x_fixed + 32 * b, kc, full);
-                        tma_load_2d(st + 2 * kOperandBytes + b * 4096, &map_yhi, 32 * b, kc, full);
-                        tma_load_2d(st + 3 * kOperandBytes + b * 4096, &map_ylo, 32 * b, kc, full);
+                    for (int b = 0; b < 4; ++b) {                                         // dZ in 32-column blocks
+                        tma_load_2d(st + kOperandBytes + b * 4096, &map_yhi, 32 * b, kc, full);
+                        tma_load_2d(st + 2 * kOperandBytes + b * 4096, &map_ylo, 32 * b, kc, full);
                     }
                 }
+                TC_TRACE(1, c);
             }
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
+        // The whole warp runs the loop (waits are warp-uniform); one elected lane issues.  Descriptors
+        // are base + small offset so that each tcgen05.mma costs a couple of uniform-datapath adds.
         constexpr uint32_t idesc = make_idesc(TN);
+        const uint64_t yh_base = TN ? make_desc(base + kOperandBytes, 4096, 512, 1u) : make_desc(base + kOperandBytes, 16, 1024);
+        const uint32_t d_corr = tmem + (uint32_t)kMainAccs * kTile;
+        const bool leader = elect_one();
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % kStages, it = c / kStages;
-            mbar_wait(bars + 8 * s, it & 1);                   // TMA bytes (Y tiles) landed
-            mbar_wait(bars + 8 * (kStages + s), it & 1);       // X split done
+            const int a = c % kASlots;
+            mbar_wait(bars + 8 * (kBarFull + s), it & 1);      // Y_hi / Y_lo tiles landed in shared memory
+            mbar_wait(bars + 8 * (kBarYReady + s), it & 1);    // A slot in tensor memory written
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t st = base + s * kStageBytes;
-                const uint32_t x_hi = st, x_lo = st + kOperandBytes, y_hi = st + 2 * kOperandBytes,
-                               y_lo = st + 3 * kOperandBytes;
+            TC_TRACE(7, c);
+            if (leader) {
+                const uint32_t a_hi = tmem_a + a * kASlotCols, a_lo = a_hi + kChunk;
+                const uint64_t yh0 = yh_base + (uint64_t)((s * kStageBytes) >> 4);
+                const uint64_t yl0 = yh0 + (uint64_t)(kOperandBytes >> 4);
 #pragma unroll
                 for (int j = 0; j < kChunk / 8; ++j) {         // UMMA_K = 8 for tf32
-                    uint64_t dxh, dxl, dyh, dyl;
-                    if (!TN) {                                 // K-major: advance 32 B inside the swizzle row
-                        dxh = make_desc(x_hi + 32 * j, 16, 1024); dxl = make_desc(x_lo + 32 * j, 16, 1024);
-                        dyh = make_desc(y_hi + 32 * j, 16, 1024); dyl = make_desc(y_lo + 32 * j, 16, 1024);
-                    } else {                                   // MN-major: advance one 8-deep k group
-                        dxh = make_desc(x_hi + 1024 * j, 4096, 512, 1u); dxl = make_desc(x_lo + 1024 * j, 4096, 512, 1u);
-                        dyh = make_desc(y_hi + 1024 * j, 4096, 512, 1u); dyl = make_desc(y_lo + 1024 * j, 4096, 512, 1u);
-                    }
+                    // K-major W: advance 32 B inside the swizzle row; N-major dZ: one 8-deep k group (1024 B)
+                    const uint64_t dyh = yh0 + (uint64_t)((TN ? 1024 * j : 32 * j) >> 4);
+                    const uint64_t dyl = yl0 + (uint64_t)((TN ? 1024 * j : 32 * j) >> 4);
                     const int ks = c * (kChunk / 8) + j;       // k-step index within this CTA
                     const uint32_t d_main = tmem + (uint32_t)(ks % kMainAccs) * kTile;
-                    const uint32_t d_corr = tmem + (uint32_t)kMainAccs * kTile;
                     const uint32_t acc_main = ks >= kMainAccs ? 1u : 0u, acc_corr = ks ? 1u : 0u;
-                    if (!TN) {                                 // A = X (rows), B = W
-                        umma_tf32(d_corr, dxl, dyh, idesc, acc_corr);
-                        umma_tf32(d_corr, dxh, dyl, idesc, 1u);
-                        umma_tf32(d_main, dxh, dyh, idesc, acc_main);
-                    } else {                                   // A = dZ^T (d_out), B = X (cols)
-                        umma_tf32(d_corr, dyl, dxh, idesc, acc_corr);
-                        umma_tf32(d_corr, dyh, dxl, idesc, 1u);
-                        umma_tf32(d_main, dyh, dxh, idesc, acc_main);
+                    if (!(g.debug & 1)) {
+                    umma_tf32_ts(d_corr, a_lo + 8 * j, dyh, idesc, acc_corr);
+                    umma_tf32_ts(d_corr, a_hi + 8 * j, dyl, idesc, 1u);
+                    umma_tf32_ts(d_main, a_hi + 8 * j, dyh, idesc, acc_main);
                     }
                 }
-                umma_commit(bars + 8 * (2 * kStages + s));     // stage reusable once these MMAs retire
-                if (c == nchunks - 1) umma_commit(bars + 8 * 3 * kStages);
+                umma_commit(bars + 8 * (kBarEmpty + s));       // smem stage AND TMEM A slot reusable once these retire
+                if (c == nchunks - 1) umma_commit(bars + 8 * kBarAccum);
+                TC_TRACE(8, c);
             }
             __syncwarp();
         }
     } else {
-        // ---------------------------------------------------------------- splitter + epilogue
-        const int t = threadIdx.x - 64;                        // 0..127
-        for (int c = 0; c < nchunks; ++c) {
+        // ---------------------------------------------------------------- X splitters (2 groups) + epilogue
+        // group 0 (warps 2..5) takes the even chunks and TMEM A slot 0, group 1 (warps 6..9) the odd
+        // chunks and slot 1: each group has two chunk periods for its load -> split -> tcgen05.st chain
+        const int grp = (warp - 2) >> 2;
+        const int q = warp & 3;                                // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;                         // A/accumulator row handled by this thread
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t slot = tmem_a + lane_base + grp * kASlotCols;
+        for (int c = grp; c < nchunks; c += kASlots) {
             const int s = c % kStages, it = c / kStages;
-            mbar_wait(bars + 8 * s, it & 1);
-            float4* xh = reinterpret_cast<float4*>(gen_base + s * kStageBytes);
-            float4* xl = reinterpret_cast<float4*>(gen_base + s * kStageBytes + kOperandBytes);
+            mbar_wait(bars + 8 * (kBarFull + s), it & 1);
+            if (q == 2) TC_TRACE(4, c);
+            const uint8_t* xs = gen_base + s * kStageBytes;
 #pragma unroll
-            for (int u = 0; u < kOperandBytes / 16 / 128; ++u) {
-                const int e = t + u * 128;
-                const float4 v = xh[e];
-                float4 h, l;
-                split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                xh[e] = h;
-                xl[e] = l;
+            for (int half = 0; half < 2; ++half) {
+                uint32_t hi[16], lo[16];
+                if (g.debug & 2) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) { hi[k] = 0; lo[k] = 0; }
+                } else if (!TN) {
+                    // row `row` of the SWIZZLE_128B tile: 16-B chunk j sits at position j ^ (row % 8)
+                    const float4* xr = reinterpret_cast<const float4*>(xs + row * 128);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 v = xr[(4 * half + j) ^ (row & 7)];
+                        float h, l;
+                        split_tf32(v.x, h, l); hi[4 * j] = __float_as_uint(h); lo[4 * j] = __float_as_uint(l);
+                        split_tf32(v.y, h, l); hi[4 * j + 1] = __float_as_uint(h); lo[4 * j + 1] = __float_as_uint(l);
+                        split_tf32(v.z, h, l); hi[4 * j + 2] = __float_as_uint(h); lo[4 * j + 2] = __float_as_uint(l);
+                        split_tf32(v.w, h, l); hi[4 * j + 3] = __float_as_uint(h); lo[4 * j + 3] = __float_as_uint(l);
+                    }
+                } else {
+                    // column `row` of the linear [32 rows][128 cols] tile (lanes read consecutive words)
+                    const float* xc = reinterpret_cast<const float*>(xs) + row + (16 * half) * kTile;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        float h, l;
+                        split_tf32(xc[k * kTile], h, l);
+                        hi[k] = __float_as_uint(h); lo[k] = __float_as_uint(l);
+                    }
+                }
+                if (half == 0 && c >= kASlots) {
+                    // the slot was last read by the MMAs of chunk c-2, whose retirement is what frees that
+                    // chunk's smem stage -- wait on the same barrier instead of a second tcgen05.commit
+                    const int cp = c - kASlots;
+                    mbar_wait(bars + 8 * (kBarEmpty + cp % kStages), (cp / kStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (q == 2) TC_TRACE(5, c);
+                }
+                tmem_st16(slot + 16 * half, hi);
+                tmem_st16(slot + kChunk + 16 * half, lo);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor core reads
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            if (q == 2) TC_TRACE(6, c);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(bars + 8 * (kStages + s));
+            if (lane == 0) mbar_arrive(bars + 8 * (kBarYReady + s));   // same per-stage barrier as the Y splitter
         }
         if (nchunks > 0) {
-            mbar_wait(bars + 8 * 3 * kStages, 0);
+            mbar_wait(bars + 8 * kBarAccum, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        const int q = warp & 3;                                // TMEM lane quadrant this warp may read
-        const int row = q * 32 + lane;                         // accumulator row (lane of TMEM)
+        // epilogue: group 0 drains accumulator columns [0, 64), group 1 columns [64, 128)
 #pragma unroll 1
-        for (int cb = 0; cb < kTile / 32; ++cb) {
-            uint32_t r[32];
-            if (nchunks > 0) {                                 // sum the 4 accumulators in fp32 (RN)
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb * 32, r);
+        for (int cb = grp * 4; cb < grp * 4 + 4; ++cb) {       // 16-column blocks
+            uint32_t r[16];
+            if (nchunks > 0) {                                 // sum the accumulators in fp32 (RN)
+                tmem_ld16(tmem + lane_base + cb * 16, r);
 #pragma unroll 1
-                for (int a = 1; a < kAccs; ++a) {
-                    uint32_t t2[32];
-                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + a * kTile + cb * 32, t2);
+                for (int acc = 1; acc < kAccs; ++acc) {
+                    uint32_t t2[16];
+                    tmem_ld16(tmem + lane_base + acc * kTile + cb * 16, t2);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(t2[i]));
+                    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(t2[i]));
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) r[i] = 0u;
+                for (int i = 0; i < 16; ++i) r[i] = 0u;
             }
             if (!TN) {
                 const int grow = x_fixed + row;
                 if (grow < n) {
-                    float* dst = g.out + (int64_t)grow * g.ld_out + cb * 32;
+                    float* dst = g.out + (int64_t)grow * g.ld_out + cb * 16;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
+                    for (int i = 0; i < 16; i += 4) {
                         float4 v = make_float4(gs_apply_act(__uint_as_float(r[i]), g.act),
                                                gs_apply_act(__uint_as_float(r[i + 1]), g.act),
                                                gs_apply_act(__uint_as_float(r[i + 2]), g.act),
@@ -291,17 +403,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     }
                 }
             } else {
-                float* dst = g.out + (int64_t)blockIdx.y * g.split_stride + (int64_t)row * g.ld_out + x_fixed + cb * 32;
+                // thread = column (x_fixed + row) of X, registers = 16 d_out rows of dW: transposed store,
+                // consecutive lanes write consecutive columns -> one 128-B line per d_out row per warp
+                const int col = x_fixed + row;
+                if (col < g.k_in) {
+                    float* dst = g.out + (int64_t)blockIdx.y * g.split_stride + (int64_t)(cb * 16) * g.ld_out + col;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const int col = x_fixed + cb * 32 + i;
-                    if (col + 4 <= g.k_in) {
-                        *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
-                                                                         __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-                    } else {
-                        for (int e = 0; e < 4; ++e)
-                            if (col + e < g.k_in) dst[i + e] = __uint_as_float(r[i + e]);
-                    }
+                    for (int i = 0; i < 16; ++i) dst[(int64_t)i * g.ld_out] = __uint_as_float(r[i]);
                 }
             }
         }
@@ -310,11 +418,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kAccs * kTile));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
     }
 }
 
-// W -> (W_hi, W_lo) and dz = gh * act'(h) -> (dz_hi, dz_lo): the pre-split "Y" operands.
+// W -> (W_hi, W_lo): the pre-split B operand of the forward GEMM (d_out x k_in, tiny)
 __global__ void split_rows_kernel(const float* __restrict__ src, int64_t ld_src, int rows, int cols,
                                   float* __restrict__ hi, float* __restrict__ lo, int64_t ld_dst) {
     const int64_t total = (int64_t)rows * cols;
@@ -327,17 +435,26 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int64_t ld_src,
     }
 }
 
-__global__ void act_grad_split_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restrict__ gh, int64_t ld_gh,
-                                      int d, int act, int n_max, const int32_t* __restrict__ n_dev,
-                                      float* __restrict__ hi, float* __restrict__ lo) {
+// dz = gh * act'(h) -> (dz_hi, dz_lo) for the rows below *n_dev, zeros above (d % 4 == 0, 128-bit accesses)
+__global__ void act_grad_rows_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restrict__ gh, int64_t ld_gh,
+                                     int d, int act, int n_max, const int32_t* __restrict__ n_dev,
+                                     float* __restrict__ hi, float* __restrict__ lo) {
     const int n = gs_row_count(n_max, n_dev);
-    const int64_t total = (int64_t)n_max * d;
+    const int d4 = d >> 2;
+    const int64_t total = (int64_t)n_max * d4;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int i = (int)(e / d), j = (int)(e - (int64_t)i * d);
-        float a = 0.f, b = 0.f;
-        if (i < n) split_tf32(gh[(int64_t)i * ld_gh + j] * gs_act_grad(h[(int64_t)i * ld_h + j], act), a, b);
-        hi[e] = a;
-        lo[e] = b;
+        const int i = (int)(e / d4), j = (int)(e - (int64_t)i * d4) * 4;
+        float4 oh = make_float4(0.f, 0.f, 0.f, 0.f), ol = oh;
+        if (i < n) {
+            const float4 a = *reinterpret_cast<const float4*>(h + (int64_t)i * ld_h + j);
+            const float4 b = *reinterpret_cast<const float4*>(gh + (int64_t)i * ld_gh + j);
+            split_tf32(b.x * gs_act_grad(a.x, act), oh.x, ol.x);
+            split_tf32(b.y * gs_act_grad(a.y, act), oh.y, ol.y);
+            split_tf32(b.z * gs_act_grad(a.z, act), oh.z, ol.z);
+            split_tf32(b.w * gs_act_grad(a.w, act), oh.w, ol.w);
+        }
+        *reinterpret_cast<float4*>(hi + (int64_t)i * d + j) = oh;
+        *reinterpret_cast<float4*>(lo + (int64_t)i * d + j) = ol;
     }
 }
 
@@ -385,14 +502,17 @@ int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64
 }
 
 int tn_splits(int n_max, int k_in) {
-    // enough splits to fill the SMs, and never more than kMaxChunksPerSplit stages accumulated in
-    // one CTA (bounds the round-toward-zero accumulation bias, see kMainAccs)
+    // Enough splits that (a) no CTA accumulates more than kMaxChunksPerSplit stages (bounds the
+    // round-toward-zero accumulation bias, see kMainAccs) and (b) tiles x splits fills whole
+    // waves of 148 CTAs (1 CTA/SM): the split count is rounded up to the end of the last wave.
     constexpr int kMaxChunksPerSplit = 32;
     const int tiles = (k_in + kTile - 1) / kTile;
-    int s = (GS_NUM_SMS + tiles - 1) / tiles;
-    const int need = (n_max + kMaxChunksPerSplit * kChunk - 1) / (kMaxChunksPerSplit * kChunk);
+    int need = (n_max + kMaxChunksPerSplit * kChunk - 1) / (kMaxChunksPerSplit * kChunk);
+    if (need < 1) need = 1;
+    const int waves = (tiles * need + GS_NUM_SMS - 1) / GS_NUM_SMS;
+    int s = waves * GS_NUM_SMS / tiles;
     if (s < need) s = need;
-    const int cap = (n_max + 4 * kChunk - 1) / (4 * kChunk);
+    const int cap = (n_max + 4 * kChunk - 1) / (4 * kChunk);       // at least 4 stages of work per CTA
     if (s > cap) s = cap;
     return s < 1 ? 1 : s;
 }
@@ -411,7 +531,7 @@ extern "C" int gs_encoder_tc_supported(int32_t k_in, int32_t d_out) {
 
 // floats of workspace for the forward: W_hi + W_lo
 extern "C" int64_t gs_encoder_fwd_tc_ws_floats(int32_t k_in, int32_t d_out) {
-    return 2 * (int64_t)d_out * ((k_in + 3) & ~3);
+    return 2 * (int64_t)d_out * ((k_in + 3) & ~3);      // W_hi + W_lo
 }
 
 extern "C" int gs_encoder_fwd_tc(const float* x, int64_t ld_x, const float* w, int64_t ld_w,
@@ -440,7 +560,8 @@ extern "C" int gs_encoder_fwd_tc(const float* x, int64_t ld_x, const float* w, i
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    TcArgs g{n_max, n_dev, k_in, act, h, ld_h, 0, 0};
+    TcArgs g{n_max, n_dev, k_in, act, h, ld_h, 0, 0, getenv("GSAGE_TC_DEBUG") ? atoi(getenv("GSAGE_TC_DEBUG")) : 0,
+             getenv("GSAGE_TC_TRACE") ? (long long*)strtoull(getenv("GSAGE_TC_TRACE"), nullptr, 10) : nullptr};
     tc_gemm_kernel<false><<<(n_max + kTile - 1) / kTile, kThreads, kSmemBytes, s>>>(mx, mh, ml, g);
     GS_LAUNCH_CHECK();
     return GS_OK;
@@ -458,15 +579,16 @@ extern "C" int gs_encoder_wgrad_tc(const float* x, int64_t ld_x, const float* h,
                                    float* gw, int64_t ld_gw, float* ws, void* stream) {
     if (!x || !h || !gh || !gw || !ws || n_max < 0) return GS_EINVAL;
     if (!gs_encoder_tc_supported(k_in, d_out)) return GS_ENOSUP;
-    if (!gs_aligned16(x) || !gs_aligned16(ws) || (ld_x & 3)) return GS_EALIGN;
+    if (!gs_aligned16(x) || !gs_aligned16(ws) || !gs_aligned16(h) || !gs_aligned16(gh) || (ld_x & 3) || (ld_h & 3) || (ld_gh & 3))
+        return GS_EALIGN;
     if (n_max == 0) return GS_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t ldw = (k_in + 3) & ~3;
     float* dz_hi = ws;
     float* dz_lo = ws + (int64_t)n_max * d_out;
     float* part = ws + 2 * (int64_t)n_max * d_out;
-    act_grad_split_kernel<<<grid1d((int64_t)n_max * d_out), 256, 0, s>>>(h, ld_h, gh, ld_gh, d_out, act, n_max, n_dev,
-                                                                        dz_hi, dz_lo);
+    act_grad_rows_kernel<<<grid1d((int64_t)n_max * (d_out / 4)), 256, 0, s>>>(h, ld_h, gh, ld_gh, d_out, act, n_max, n_dev,
+                                                                             dz_hi, dz_lo);
     GS_LAUNCH_CHECK();
     const int splits = tn_splits(n_max, k_in);
     int rps = (n_max + splits - 1) / splits;
@@ -474,7 +596,7 @@ extern "C" int gs_encoder_wgrad_tc(const float* x, int64_t ld_x, const float* h,
     CUtensorMap mx, mh, ml;
     int rc;
     const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;    // MN-major tf32 operand layout
-    if ((rc = make_map(&mx, x, n_max, k_in, ld_x, 32, kChunk, swz))) return rc;
+    if ((rc = make_map(&mx, x, n_max, k_in, ld_x, kTile, kChunk, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
     if ((rc = make_map(&mh, dz_hi, n_max, d_out, d_out, 32, kChunk, swz))) return rc;
     if ((rc = make_map(&ml, dz_lo, n_max, d_out, d_out, 32, kChunk, swz))) return rc;
     static bool attr_set = false;
@@ -483,7 +605,7 @@ extern "C" int gs_encoder_wgrad_tc(const float* x, int64_t ld_x, const float* h,
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    TcArgs g{n_max, n_dev, k_in, GS_ACT_NONE, part, ldw, rps, (int64_t)d_out * ldw};
+    TcArgs g{n_max, n_dev, k_in, GS_ACT_NONE, part, ldw, rps, (int64_t)d_out * ldw, getenv("GSAGE_TC_DEBUG") ? atoi(getenv("GSAGE_TC_DEBUG")) : 0, nullptr};
     dim3 grid((k_in + kTile - 1) / kTile, splits);
     tc_gemm_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(mx, mh, ml, g);
     GS_LAUNCH_CHECK();

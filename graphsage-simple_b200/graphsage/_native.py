@@ -29,6 +29,7 @@ SIGNATURES = {
     "gs_encoder_bwd_ws_floats": (_i64, [_i32, _i32, _i32]),
     "gs_encoder_bwd": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr,
                               _ptr, _ptr, _i64, _ptr, _i64, _ptr, _ptr]),
+    "gs_encoder_dgrad": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _i64, _ptr]),
     "gs_encoder_tc_supported": (_i32, [_i32, _i32]),
     "gs_encoder_fwd_tc_ws_floats": (_i64, [_i32, _i32]),
     "gs_encoder_fwd_tc": (_i32, [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _i64, _ptr, _ptr]),

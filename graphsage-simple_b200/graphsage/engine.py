@@ -94,9 +94,13 @@ class TrainEngine:
         self.xent_ws = torch.empty(ops.classifier_ws_floats(B, self.d2, self.C), device=dev)
         # layer 1 runs on the tcgen05 path when the shape qualifies (d1 == 128, K1 % 4 == 0)
         self.tc1 = ops.encoder_tc_supported(self.K1, self.d1)
+        self.tc2 = ops.encoder_tc_supported(self.K2, self.d2) and B >= 512
+        need = [4]
         if self.tc1:
-            self.tc_ws = torch.empty(max(ops.encoder_fwd_tc_ws_floats(self.K1, self.d1),
-                                         ops.encoder_wgrad_tc_ws_floats(n1_max, self.K1, self.d1)), device=dev)
+            need += [ops.encoder_fwd_tc_ws_floats(self.K1, self.d1), ops.encoder_wgrad_tc_ws_floats(n1_max, self.K1, self.d1)]
+        if self.tc2:
+            need += [ops.encoder_fwd_tc_ws_floats(self.K2, self.d2), ops.encoder_wgrad_tc_ws_floats(B, self.K2, self.d2)]
+        self.tc_ws = torch.empty(max(need), device=dev)
         # parameters + gradients: one flat block each (padded rows), module params alias into it
         shapes = [(self.d1, self.K1), (self.d2, self.K2), (self.C, self.d2)]
         sizes = [r * ops.round4(c) for r, c in shapes]
@@ -171,11 +175,18 @@ class TrainEngine:
         comb2, h2 = self.comb2[:b], self.h2[:b]
         ops.gather_mean_fwd(self.h1, self.d1, idx2, cnt2, comb2, neigh_off=0 if self.gcn else self.d1,
                             self_ids=None if self.gcn else self.self2[:b])
-        ops.encoder_fwd(comb2, self.w2, self.act2, h2)
+        if self.tc2:
+            ops.encoder_fwd_tc(comb2, self.w2, self.act2, h2, ws=self.tc_ws)
+        else:
+            ops.encoder_fwd(comb2, self.w2, self.act2, h2)
         ops.classifier_xent(h2, self.wc, labels, 1.0, self.logits[:b], self.loss, self.gh2[:b], self.gwc,
                             ws=self.xent_ws)
-        ops.encoder_bwd(comb2, self.w2, h2, self.gh2[:b], self.act2, self.gw2, self.gcomb2[:b], dz=self.dz2,
-                        ws=self.ws)
+        if self.tc2:
+            ops.encoder_wgrad_tc(comb2, h2, self.gh2[:b], self.act2, self.gw2, ws=self.tc_ws)
+            ops.encoder_dgrad(self.w2, h2, self.gh2[:b], self.act2, self.gcomb2[:b], dz=self.dz2)
+        else:
+            ops.encoder_bwd(comb2, self.w2, h2, self.gh2[:b], self.act2, self.gw2, self.gcomb2[:b], dz=self.dz2,
+                            ws=self.ws)
         gh1 = self.gh1[:n1_max]
         gh1.zero_()
         ops.scatter_mean_bwd(self.gcomb2[:b], self.d1, idx2, cnt2, self.gh1, neigh_off=0 if self.gcn else self.d1,

@@ -162,6 +162,21 @@ def encoder_bwd(x, w, h, gh, act, gw, gx=None, dz=None, ws=None, n_dev=None):
     return gw, gx
 
 
+def encoder_dgrad(w, h, gh, act, gx, dz=None, n_dev=None):
+    """gx = (gh * act'(h)) . w -- the input gradient of K3 alone."""
+    lib = N.load()
+    N.require_cuda(w, h, gh, gx)
+    n_max, d_out = h.shape
+    k_in = w.shape[1]
+    if dz is None:
+        dz = torch.empty((max(n_max, 1), round4(d_out)), device=h.device, dtype=torch.float32)
+    N.check(lib.gs_encoder_dgrad(N.ptr(w), w.stride(0), N.ptr(h), h.stride(0), N.ptr(gh), gh.stride(0), k_in, d_out,
+                                 int(act), n_max, N.ptr(n_dev), N.ptr(dz), N.ptr(gx), gx.stride(0), N.stream()),
+            "gs_encoder_dgrad")
+    LAUNCHES[0] += 2
+    return gx
+
+
 def encoder_tc_supported(k_in, d_out):
     return bool(N.load().gs_encoder_tc_supported(int(k_in), int(d_out)))
 

@@ -122,6 +122,12 @@ GS_API int gs_encoder_bwd(const float* x, int64_t ld_x, const float* w, int64_t 
                    float* dz, float* gw, int64_t ld_gw, float* gx, int64_t ld_gx,
                    float* ws, void* stream);
 
+/* Input gradient alone: dz = gh * act'(h) (dz [n_max, round_up(d_out,4)]), gx[n, k_in] = dz . w.   */
+GS_API int gs_encoder_dgrad(const float* w, int64_t ld_w, const float* h, int64_t ld_h,
+                     const float* gh, int64_t ld_gh, int32_t k_in, int32_t d_out, int32_t act,
+                     int32_t n_max, const int32_t* n_dev, float* dz, float* gx, int64_t ld_gx,
+                     void* stream);
+
 /* ---- K3 on tcgen05 tensor cores (3xTF32, fp32 accumulation in TMEM) ------------------------
  * Same contracts as gs_encoder_fwd and the gw part of gs_encoder_bwd, for the shapes
  * gs_encoder_tc_supported() accepts (d_out == 128, k_in % 4 == 0).  The three-term hi/lo
