@@ -22,6 +22,7 @@ import time
 
 import numpy as np
 
+os.environ["NCCL_DEBUG"] = os.environ.get("GSAGE_NCCL_DEBUG", "WARN")   # keep NCCL banners off stdout (ONE JSON line)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "graphsage-simple_b200")):
     if p not in sys.path:
@@ -239,8 +240,10 @@ def run_b200(args):
     allreduce = None
     lr = args.lr
     if world > 1:
-        allreduce = lambda flat: dist.all_reduce(flat)
-        lr = args.lr / world               # mean over the global batch = sum of rank means / world
+        from graphsage import dist as gdist
+        allreduce = gdist.make_allreduce()
+        lr = gdist.dp_lr(args.lr, world)   # mean over the global batch = sum of rank means / world
+        eng.grad_scale = gdist.local_grad_scale(B, B * world, world)
 
     # ---- (1) device-resident throughput: inputs already in HBM, one graph replay per step.
     # Steps are software-pipelined: while batch i is in its GEMM/backward chain the sample ->

@@ -117,6 +117,7 @@ class TrainEngine:
         self._warm = set()
         self._launch_count = {}
         self._side = None
+        self.grad_scale = 1.0      # data parallel: n_local * world / n_global (dist.local_grad_scale)
 
     # convenience views of the current frontier set (tests / bench read these)
     @property
@@ -179,7 +180,7 @@ class TrainEngine:
             ops.encoder_fwd_tc(comb2, self.w2, self.act2, h2, ws=self.tc_ws)
         else:
             ops.encoder_fwd(comb2, self.w2, self.act2, h2)
-        ops.classifier_xent(h2, self.wc, labels, 1.0, self.logits[:b], self.loss, self.gh2[:b], self.gwc,
+        ops.classifier_xent(h2, self.wc, labels, self.grad_scale, self.logits[:b], self.loss, self.gh2[:b], self.gwc,
                             ws=self.xent_ws)
         if self.tc2:
             ops.encoder_wgrad_tc(comb2, h2, self.gh2[:b], self.act2, self.gw2, ws=self.tc_ws)
@@ -206,14 +207,18 @@ class TrainEngine:
     def _update(self, lr):
         ops.sgd_step(self.flat_w, self.flat_g, lr)
 
-    def _overlapped(self, parity, b, b_next, lr):
+    def _overlapped(self, parity, b, b_next, lr, allreduce=None):
         """compute chain of set[parity] on the current stream || gather chain of set[1-parity] on a
-        side stream (fork/join, so the pair is one CUDA graph); lr=None leaves SGD to the caller."""
+        side stream (fork/join, so the pair is one CUDA graph); lr=None leaves SGD to the caller.
+        With ``allreduce`` the gradient all-reduce is enqueued between backward and SGD on the
+        main stream, i.e. it also overlaps the side stream's gather chain."""
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
             self._gather_chain(self.sets[1 - parity], b_next)
         self._compute_chain(self.sets[parity], b)
+        if allreduce is not None:
+            allreduce(self.flat_g)
         if lr is not None:
             self._update(lr)
         main.wait_stream(self._side)
@@ -245,7 +250,8 @@ class TrainEngine:
         whole = [v for k, v in c.items() if k[0] in ("step", "pipe")]
         if whole:
             return max(whole)
-        return max([v for k, v in c.items() if k[0] in ("fb", "pipe_fb")] or [0]) + \
+        parts = max([v for k, v in c.items() if k[0] == "gchain"] or [0]) + max([v for k, v in c.items() if k[0] == "cchain"] or [0])
+        return max(max([v for k, v in c.items() if k[0] == "fb"] or [0]), parts) + \
             max([v for k, v in c.items() if k[0] == "sgd"] or [0])
 
     def stage(self, nodes, labels, step, slot=None):
@@ -315,9 +321,18 @@ class TrainEngine:
         if allreduce is None:
             self._run(("pipe", b, b_next, float(lr), p), lambda: self._overlapped(p, b, b_next, lr))
         else:
-            self._run(("pipe_fb", b, b_next, p), lambda: self._overlapped(p, b, b_next, None))
+            # data parallel: the NCCL all-reduce is enqueued eagerly (capturing a collective inside a
+            # forked graph deadlocked across ranks), so the two chains are separate graphs on two
+            # streams: the next batch's gather chain runs on the side stream while the main stream
+            # does compute -> all-reduce -> SGD.
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self._run(("gchain", b_next, 1 - p), lambda: self._gather_chain(self.sets[1 - p], b_next))
+            self._run(("cchain", b, p), lambda: self._compute_chain(self.sets[p], b))
             allreduce(self.flat_g)
             self.update(lr)
+            main.wait_stream(self._side)
         self.cur = 1 - p
 
     def read_loss(self):
