@@ -52,7 +52,8 @@ gather_mean_kernel(const float* __restrict__ table, int64_t ld_table, int dim,
     const int nchunks = (dim + 3) >> 2;
     // grid-stride over rows: the grid is capped at a fixed number of blocks per SM so that the
     // kernel leaves room for a co-resident tensor-core CTA (engine.py pipelining)
-    for (int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < n; row += gridDim.x * kWarpsPerBlock) {
+    const int wpb = blockDim.x >> 5;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < n; row += gridDim.x * wpb) {
     const int c = min(cnt[row], width);
     const float inv = c > 0 ? 1.f / (float)c : 0.f;
     float* orow = out + (int64_t)row * ld_out;
@@ -192,23 +193,34 @@ extern "C" int gs_gather_mean_fwd(const float* table, int64_t ld_table, int32_t 
     if (n_max == 0) return GS_OK;
     const int align = (neigh_off & 3) == 0 ? 4 : ((neigh_off & 1) == 0 ? 2 : 1);
     const int nchunks = (dim + 3) / 4;
-    static int bps = 0;                 // blocks per SM cap (GSAGE_GATHER_BPS, default 2: leaves room for a co-resident tcgen05 CTA)
+    // Register budget of an SM (64 K): the gather must leave room for a co-resident tcgen05 GEMM CTA
+    // (320 threads x 72 regs = 23 K) or the fused head (256 x 96 = 24.6 K) AND a sampler block (8 K):
+    // 3 blocks of 4 warps x 80 regs = 30.7 K, i.e. 12 warps x 10 independent 128-bit loads per lane
+    // = 61 KB in flight per SM (Little: 6.5 TB/s x ~800 ns / 148 SMs = 35 KB).  Tunable for experiments.
+    static int bps = 0, wpb = 0, carve = 0;
     if (bps == 0) {
+        // max-shared carveout: measured 0.292 ms/step vs 0.349 with the default split (the SM's split can only
+        // change when it is idle, so an L1-heavy resident gather keeps the 198 KB GEMM CTAs out); costs the
+        // gather ~10 % stand-alone (fewer outstanding L1 requests).  profiles/README.md, r01 sweep.
+        carve = getenv("GSAGE_GATHER_CARVEOUT") ? atoi(getenv("GSAGE_GATHER_CARVEOUT")) : 1;
         const char* e = getenv("GSAGE_GATHER_BPS");
-        bps = e ? atoi(e) : 2;
+        bps = e ? atoi(e) : 3;
         if (bps < 1) bps = 1;
+        e = getenv("GSAGE_GATHER_WPB");
+        wpb = e ? atoi(e) : 4;
+        if (wpb < 1 || wpb > kWarpsPerBlock) wpb = 4;
     }
-    int nblocks = (n_max + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    int nblocks = (n_max + wpb - 1) / wpb;
     if (nblocks > GS_NUM_SMS * bps) nblocks = GS_NUM_SMS * bps;
-    const dim3 grid(nblocks), block(kWarpsPerBlock * 32);
+    const dim3 grid(nblocks), block(wpb * 32);
     cudaStream_t s = (cudaStream_t)stream;
-#define GS_GM(CH, NB) gather_mean_kernel<CH, NB><<<grid, block, 0, s>>>(table, ld_table, dim, idx, cnt, width, \
+#define GS_GM(CH, NB) if (carve) GS_PREFER_SMEM((gather_mean_kernel<CH, NB>)); gather_mean_kernel<CH, NB><<<grid, block, 0, s>>>(table, ld_table, dim, idx, cnt, width, \
         self_ids, n_max, n_dev, out, ld_out, neigh_off, align)
-    if (nchunks <= 32) GS_GM(1, 8);
-    else if (nchunks <= 64) GS_GM(2, 4);
-    else if (nchunks <= 96) GS_GM(3, 4);
-    else if (nchunks <= 128) GS_GM(4, 2);
-    else GS_GM(5, 2);
+    if (nchunks <= 32) { GS_GM(1, 8); }
+    else if (nchunks <= 64) { GS_GM(2, 4); }
+    else if (nchunks <= 96) { GS_GM(3, 4); }
+    else if (nchunks <= 128) { GS_GM(4, 2); }
+    else { GS_GM(5, 2); }
 #undef GS_GM
     GS_LAUNCH_CHECK();
     return GS_OK;
@@ -220,6 +232,7 @@ extern "C" int gs_gather_rows(const float* table, int64_t ld_table, int32_t dim,
     if (!gs_aligned16(table) || !gs_aligned16(out) || (ld_table & 3) || (ld_out & 3)) return GS_EALIGN;
     if (ld_table < dim || ld_out < dim) return GS_EINVAL;
     if (n_max == 0) return GS_OK;
+    GS_PREFER_SMEM(gather_rows_kernel);
     gather_rows_kernel<<<(n_max + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
         table, ld_table, dim, ids, n_max, n_dev, out, ld_out);
     GS_LAUNCH_CHECK();
@@ -235,6 +248,7 @@ extern "C" int gs_scatter_mean_bwd(const float* gout, int64_t ld_gout, int32_t n
     if (ld_gtable < dim || ld_gout < neigh_off + dim) return GS_EINVAL;
     if (n_max == 0) return GS_OK;
     const int align = (neigh_off & 3) == 0 ? 4 : 1;
+    GS_PREFER_SMEM(scatter_mean_kernel);
     scatter_mean_kernel<<<(n_max + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
         gout, ld_gout, neigh_off, dim, idx, cnt, width, self_ids, n_max, n_dev, gtable, ld_gtable, align);
     GS_LAUNCH_CHECK();
@@ -246,6 +260,7 @@ extern "C" int gs_sgd_step(float* p, const float* g, float lr, int64_t n, void* 
     if (n == 0) return GS_OK;
     int64_t blocks = (n + 255) / 256;
     if (blocks > GS_NUM_SMS * 8) blocks = GS_NUM_SMS * 8;
+    GS_PREFER_SMEM(sgd_kernel);
     sgd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, lr, n);
     GS_LAUNCH_CHECK();
     return GS_OK;

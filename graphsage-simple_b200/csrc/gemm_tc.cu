@@ -193,8 +193,9 @@ constexpr int kBarAFree = 2 * kStages + kASlots;  // [kASlots]  MMAs that read t
 constexpr int kBarAccum = 2 * kStages + 2 * kASlots;
 constexpr int kBarYReady = kBarAccum + 1;         // [kStages]  Y tile split into hi/lo in shared memory
 
+// 72 registers: 320 x 72 = 23 K leaves room for the gather blocks that share the SM (gather.cu)
 template <bool TN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(72)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_yhi,
                const __grid_constant__ CUtensorMap map_ylo, TcArgs g) {
     extern __shared__ uint8_t smem_raw[];
@@ -547,6 +548,7 @@ extern "C" int gs_encoder_fwd_tc(const float* x, int64_t ld_x, const float* w, i
     const int64_t ldw = (k_in + 3) & ~3;
     float* w_hi = ws;
     float* w_lo = ws + (int64_t)d_out * ldw;
+    GS_PREFER_SMEM(split_rows_kernel);
     split_rows_kernel<<<grid1d((int64_t)d_out * k_in), 256, 0, s>>>(w, ld_w, d_out, k_in, w_hi, w_lo, ldw);
     GS_LAUNCH_CHECK();
     CUtensorMap mx, mh, ml;
@@ -587,6 +589,8 @@ extern "C" int gs_encoder_wgrad_tc(const float* x, int64_t ld_x, const float* h,
     float* dz_hi = ws;
     float* dz_lo = ws + (int64_t)n_max * d_out;
     float* part = ws + 2 * (int64_t)n_max * d_out;
+    GS_PREFER_SMEM(act_grad_rows_kernel);
+    GS_PREFER_SMEM(tc_reduce_kernel);
     act_grad_rows_kernel<<<grid1d((int64_t)n_max * (d_out / 4)), 256, 0, s>>>(h, ld_h, gh, ld_gh, d_out, act, n_max, n_dev,
                                                                              dz_hi, dz_lo);
     GS_LAUNCH_CHECK();

@@ -12,6 +12,20 @@
         if (e__ != cudaSuccess) return (int)e__;            \
     } while (0)
 
+// Kernels that may share an SM with a tcgen05 GEMM CTA (198 KB of shared memory) or the fused head
+// (175 KB) must not pull the SM's L1/shared split towards L1: the split can only change on an idle
+// SM, so a resident zero-smem kernel with the default carveout keeps the big-smem CTAs out until it
+// drains (measured: the layer-1 GEMM waited 130 us for the gather, profiles/README.md).
+#define GS_PREFER_SMEM(kernel)                                                                        \
+    do {                                                                                              \
+        static bool done__ = false;                                                                   \
+        if (!done__) {                                                                                \
+            cudaFuncSetAttribute((kernel), cudaFuncAttributePreferredSharedMemoryCarveout,            \
+                                 (int)cudaSharedmemCarveoutMaxShared);                                \
+            done__ = true;                                                                            \
+        }                                                                                             \
+    } while (0)
+
 static inline bool gs_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __device__ __forceinline__ int gs_row_count(int n_max, const int32_t* n_dev) {

@@ -292,6 +292,7 @@ extern "C" int gs_sample_csr(const int64_t* rowptr, const int32_t* col, int32_t 
     if (k >= 0 && width < k + (add_self ? 1 : 0)) return GS_EINVAL;
     if (n_max == 0) return GS_OK;
     if (k <= 32) {
+        GS_PREFER_SMEM(sample_csr_warp_kernel);
         sample_csr_warp_kernel<<<(n_max + kWarpRows - 1) / kWarpRows, kWarpRows * 32, 0, (cudaStream_t)stream>>>(
             rowptr, col, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed, (uint32_t)(seed >> 32),
             step, step_dev, tag_head, tag_tail, n_head, idx, cnt);
@@ -323,6 +324,10 @@ extern "C" int gs_dedup_remap(int32_t* idx, const int32_t* cnt, int32_t n_max, c
     int eb = (int)((entries + 255) / 256);
     if (eb > GS_NUM_SMS * 8) eb = GS_NUM_SMS * 8;
     if (eb < 1) eb = 1;
+    GS_PREFER_SMEM(dedup_mark_kernel);
+    GS_PREFER_SMEM(dedup_count_kernel);
+    GS_PREFER_SMEM(dedup_compact_kernel);
+    GS_PREFER_SMEM(dedup_remap_kernel);
     dedup_mark_kernel<<<eb, 256, 0, s>>>(idx, cnt, n_max, n_dev, width, slot_of);
     GS_LAUNCH_CHECK();
     dedup_count_kernel<<<nb, kScanThreads, 0, s>>>(slot_of, num_nodes, nb, block_counts, slot_base, n_total_dev);

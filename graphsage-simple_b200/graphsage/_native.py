@@ -39,8 +39,15 @@ SIGNATURES = {
     "gs_classifier_ws_floats": (_i64, [_i32, _i32, _i32]),
     "gs_classifier_xent": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i32, _i32, _i32, _f32, _ptr, _i64, _ptr,
                                   _ptr, _i64, _ptr, _i64, _ptr, _ptr]),
+    "gs_head_supported": (_i32, [_i32, _i32, _i32, _i32]),
+    "gs_head_ws_floats": (_i64, [_i32, _i32, _i32]),
+    "gs_head_fwd_bwd": (_i32, [_ptr, _i64, _i32, _ptr, _ptr, _i32, _ptr, _ptr, _i64, _i32, _i32, _ptr, _i64, _i32,
+                               _ptr, _i32, _f32, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64,
+                               _ptr, _i64, _ptr, _ptr]),
     "gs_sgd_step": (_i32, [_ptr, _ptr, _f32, _i64, _ptr]),
     "gs_gather_rows": (_i32, [_ptr, _i64, _i32, _ptr, _i32, _ptr, _ptr, _i64, _ptr]),
+    "gs_bucket_scratch_ints": (_i32, [_i32, _i32]),
+    "gs_bucket_by_owner": (_i32, [_ptr, _i32, _ptr, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "gs_advance_step": (_i32, [_ptr, _ptr]),
 }
 

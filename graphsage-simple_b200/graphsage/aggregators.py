@@ -94,15 +94,14 @@ class MeanAggregator(nn.Module):
             else:
                 idx, cnt, num_ids = self._tile_plain(nodes, to_neighs, num_sample, dev)
         else:
-            if not isinstance(graph, CSRGraph):
+            if not hasattr(graph, "sample"):
                 raise TypeError("MeanAggregator.forward needs to_neighs (list of sets) or graph=CSRGraph")
             ids = ops.as_ids(nodes, dev)
             width = None
             if num_sample is None:
                 width = graph.max_degree + (1 if self.gcn else 0)
-            idx, cnt = ops.sample_csr(graph.rowptr, graph.col, graph.num_nodes, ids, num_sample,
-                                      add_self=self.gcn, seed=sampling.get_seed(), step=sampling.get_step(),
-                                      tag_head=self._next_tag(), width=width)
+            idx, cnt = graph.sample(ids, num_sample, add_self=self.gcn, seed=sampling.get_seed(),
+                                    step=sampling.get_step(), tag=self._next_tag(), width=width)
             num_ids = graph.num_nodes
         # dedup (aggregators.py:52-53) and lookup of the distinct rows (aggregators.py:62-65)
         uniq, n_total = ops.dedup_remap(idx, cnt, self._dedup_scratch(num_ids, dev))

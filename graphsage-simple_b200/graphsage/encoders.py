@@ -41,7 +41,7 @@ class Encoder(nn.Module):
         init.xavier_uniform_(self.weight)                          # encoders.py:36
         if verbose:
             print("feat dim:", self.feat_dim, "embed_dim:", self.embed_dim)   # encoders.py:38
-        self._graph = adj_lists if isinstance(adj_lists, CSRGraph) else None
+        self._graph = adj_lists if hasattr(adj_lists, "sample") else None      # CSRGraph / ShardedCSR
 
     @property
     def graph(self):

@@ -25,9 +25,9 @@ _SIGMOID = ("node_degree", "shared", "pagerank")
 
 
 class _FrontierSet:
-    """Everything one minibatch's sample -> gather chain produces, plus its staged inputs.  Two
-    sets exist so that the chain for batch t+1 can run while batch t is in its GEMM/backward
-    chain (``TrainEngine.train_step_pipelined``)."""
+    """Everything one minibatch's sample -> gather chain produces, plus its staged inputs.  Three
+    sets exist when pipelining: batch t+2 is being sampled and batch t+1 gathered while batch t
+    is in its GEMM/backward chain (``TrainEngine.step_pipelined``)."""
 
     def __init__(self, eng):
         dev, B, n1_max = eng.dev, eng.B, eng.n1_max
@@ -35,6 +35,7 @@ class _FrontierSet:
         # per-step inputs: one pinned staging block [step | labels | targets] -> one H2D copy
         self.stage_host = torch.empty(8 + 8 * B + 4 * B, dtype=torch.uint8).pin_memory()
         self.stage_dev = torch.zeros(8 + 8 * B + 4 * B, dtype=torch.uint8, device=dev)
+        self.stage_event = None
         self.step_dev = self.stage_dev[:8].view(torch.int64)
         self.labels = self.stage_dev[8:8 + 8 * B].view(torch.int64)
         self.targets = self.stage_dev[8 + 8 * B:].view(torch.int32)
@@ -71,7 +72,7 @@ class TrainEngine:
         self.n1_max = n1_max
         self.K1 = self.F if self.gcn else 2 * self.F
         self.K2 = self.d1 if self.gcn else 2 * self.d1
-        self.sets = [_FrontierSet(self)]           # the second set is created on first pipelined use
+        self.sets = [_FrontierSet(self)]           # sets 2 and 3 are created on first pipelined use
         self.cur = 0
         self.loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
         self.self2 = torch.arange(B, device=dev, dtype=torch.int32)
@@ -101,6 +102,10 @@ class TrainEngine:
         if self.tc2:
             need += [ops.encoder_fwd_tc_ws_floats(self.K2, self.d2), ops.encoder_wgrad_tc_ws_floats(B, self.K2, self.d2)]
         self.tc_ws = torch.empty(max(need), device=dev)
+        # the outer layer + classifier + loss + backward as two launches when the shape qualifies
+        self.head = ops.head_supported(self.d1, self.K2, self.d2, self.C)
+        self.head_ws = ops.head_ws(B, self.K2, self.C, dev) if self.head else None
+        self._aux = None
         # parameters + gradients: one flat block each (padded rows), module params alias into it
         shapes = [(self.d1, self.K1), (self.d2, self.K2), (self.C, self.d2)]
         sizes = [r * ops.round4(c) for r, c in shapes]
@@ -116,7 +121,8 @@ class TrainEngine:
         self._graphs = {}
         self._warm = set()
         self._launch_count = {}
-        self._side = None
+        self._side = self._gstream = self._sstream = None
+        self.queue = []            # batches in flight: {slot, b, state (0 staged, 1 sampled, 2 gathered), ids}
         self.grad_scale = 1.0      # data parallel: n_local * world / n_global (dist.local_grad_scale)
 
     # convenience views of the current frontier set (tests / bench read these)
@@ -139,6 +145,12 @@ class TrainEngine:
     def _gather_chain(self, fs, b):
         """sample -> dedup -> sample -> gather for the ``b`` staged targets of frontier set ``fs``:
         everything of a step that does not depend on the weights."""
+        self._sample_chain(fs, b)
+        self._gather(fs, b)
+
+    def _sample_chain(self, fs, b):
+        """Stage 1 of the pipeline: both sampled tiles and the layer-1 frontier of a staged batch
+        (latency-bound integer work, no feature bytes)."""
         seed = sampling.get_seed()
         base = self.slot_base_of(b)
         targets = fs.targets[:b]
@@ -160,8 +172,13 @@ class TrainEngine:
                        seed=seed, step_dev=fs.step_dev, tag_head=sampling.call_tag(self.uid1, 1),
                        tag_tail=sampling.call_tag(self.uid1, 0), n_head=base, n_dev=fs.n1_dev,
                        width=self.w1_width, idx=idx1, cnt=cnt1)
-        ops.gather_mean_fwd(self.table, self.F, idx1, cnt1, fs.comb1[:n1_max], neigh_off=0 if self.gcn else self.F,
-                            self_ids=None if self.gcn else fr, n_dev=fs.n1_dev)
+
+    def _gather(self, fs, b):
+        """Stage 2: the HBM-bound layer-1 gather-mean over the sampled tile -> comb1."""
+        n1_max = self._n1_max(b)
+        ops.gather_mean_fwd(self.table, self.F, fs.idx1[:n1_max], fs.cnt1[:n1_max], fs.comb1[:n1_max],
+                            neigh_off=0 if self.gcn else self.F,
+                            self_ids=None if self.gcn else fs.frontier1[:n1_max], n_dev=fs.n1_dev)
 
     def _compute_chain(self, fs, b):
         """Encoder GEMMs, classifier/loss and the whole backward for frontier set ``fs``."""
@@ -169,11 +186,27 @@ class TrainEngine:
         labels = fs.labels[:b]
         idx2, cnt2 = fs.idx2[:b], fs.cnt2[:b]
         comb1, h1 = fs.comb1[:n1_max], self.h1[:n1_max]
+        gh1 = self.gh1[:n1_max]
+        if self.head:
+            # gh1 is cleared on a forked branch, concurrently with the layer-1 GEMM
+            main = torch.cuda.current_stream()
+            if self._aux is None:
+                self._aux = torch.cuda.Stream(device=self.dev)
+            self._aux.wait_stream(main)
+            with torch.cuda.stream(self._aux):
+                gh1.zero_()
         if self.tc1:
             ops.encoder_fwd_tc(comb1, self.w1, self.act1, h1, ws=self.tc_ws, n_dev=fs.n1_dev)
         else:
             ops.encoder_fwd(comb1, self.w1, self.act1, h1, n_dev=fs.n1_dev)
         comb2, h2 = self.comb2[:b], self.h2[:b]
+        if self.head:
+            main.wait_stream(self._aux)
+            ops.head_fwd_bwd(self.h1, self.d1, idx2, cnt2, None if self.gcn else self.self2[:b], self.w2, self.act2,
+                             self.wc, labels, self.grad_scale, comb2, h2, self.logits[:b], self.loss, self.gh1,
+                             self.gw2, self.gwc, self.head_ws)
+            self._wgrad1(fs, comb1, h1, gh1)
+            return
         ops.gather_mean_fwd(self.h1, self.d1, idx2, cnt2, comb2, neigh_off=0 if self.gcn else self.d1,
                             self_ids=None if self.gcn else self.self2[:b])
         if self.tc2:
@@ -188,10 +221,12 @@ class TrainEngine:
         else:
             ops.encoder_bwd(comb2, self.w2, h2, self.gh2[:b], self.act2, self.gw2, self.gcomb2[:b], dz=self.dz2,
                             ws=self.ws)
-        gh1 = self.gh1[:n1_max]
         gh1.zero_()
         ops.scatter_mean_bwd(self.gcomb2[:b], self.d1, idx2, cnt2, self.gh1, neigh_off=0 if self.gcn else self.d1,
                              self_ids=None if self.gcn else self.self2[:b])
+        self._wgrad1(fs, comb1, h1, gh1)
+
+    def _wgrad1(self, fs, comb1, h1, gh1):
         if self.tc1:
             ops.encoder_wgrad_tc(comb1, h1, gh1, self.act1, self.gw1, ws=self.tc_ws, n_dev=fs.n1_dev)
         else:
@@ -207,21 +242,26 @@ class TrainEngine:
     def _update(self, lr):
         ops.sgd_step(self.flat_w, self.flat_g, lr)
 
-    def _overlapped(self, parity, b, b_next, lr, allreduce=None):
-        """compute chain of set[parity] on the current stream || gather chain of set[1-parity] on a
-        side stream (fork/join, so the pair is one CUDA graph); lr=None leaves SGD to the caller.
-        With ``allreduce`` the gradient all-reduce is enqueued between backward and SGD on the
-        main stream, i.e. it also overlaps the side stream's gather chain."""
+    def _overlapped(self, p, b0, b1, b2, lr):
+        """One pipelined step as a fork/join over three streams (captured as ONE CUDA graph):
+        compute chain of set p on the current stream || gather of set p+1 || sample chain of set
+        p+2.  b1 / b2 are None when the queue is shorter (tail of a run)."""
         main = torch.cuda.current_stream()
-        self._side.wait_stream(main)
-        with torch.cuda.stream(self._side):
-            self._gather_chain(self.sets[1 - parity], b_next)
-        self._compute_chain(self.sets[parity], b)
-        if allreduce is not None:
-            allreduce(self.flat_g)
+        if b1 is not None:
+            self._gstream.wait_stream(main)
+            with torch.cuda.stream(self._gstream):
+                self._gather(self.sets[(p + 1) % self.depth], b1)
+        if b2 is not None:
+            self._sstream.wait_stream(main)
+            with torch.cuda.stream(self._sstream):
+                self._sample_chain(self.sets[(p + 2) % self.depth], b2)
+        self._compute_chain(self.sets[p], b0)
         if lr is not None:
             self._update(lr)
-        main.wait_stream(self._side)
+        if b1 is not None:
+            main.wait_stream(self._gstream)
+        if b2 is not None:
+            main.wait_stream(self._sstream)
 
     # ------------------------------------------------------------------ graph capture / replay
     def _run(self, key, fn):
@@ -250,7 +290,7 @@ class TrainEngine:
         whole = [v for k, v in c.items() if k[0] in ("step", "pipe")]
         if whole:
             return max(whole)
-        parts = max([v for k, v in c.items() if k[0] == "gchain"] or [0]) + max([v for k, v in c.items() if k[0] == "cchain"] or [0])
+        parts = sum(max([v for k, v in c.items() if k[0] == nm] or [0]) for nm in ("s", "g", "cchain"))
         return max(max([v for k, v in c.items() if k[0] == "fb"] or [0]), parts) + \
             max([v for k, v in c.items() if k[0] == "sgd"] or [0])
 
@@ -262,6 +302,8 @@ class TrainEngine:
             raise ValueError("batch of %d exceeds the engine's max_batch %d" % (b, self.B))
         fs = self.sets[self.cur if slot is None else slot]
         h = fs.stage_host
+        if fs.stage_event is not None:
+            fs.stage_event.synchronize()          # the previous H2D copy out of this pinned block is done
         h[:8].view(torch.int64)[0] = int(step)
         if isinstance(labels, torch.Tensor):
             h[8:8 + 8 * b].view(torch.int64).copy_(labels.reshape(-1))
@@ -273,6 +315,9 @@ class TrainEngine:
             h[8 + 8 * self.B:8 + 8 * self.B + 4 * b].view(torch.int32).copy_(
                 torch.from_numpy(np.asarray(nodes, dtype=np.int32)))
         fs.stage_dev.copy_(h, non_blocking=True)
+        if fs.stage_event is None:
+            fs.stage_event = torch.cuda.Event()
+        fs.stage_event.record()
         return b
 
     def stage_device(self, d_nodes, d_labels, step, slot=None):
@@ -301,39 +346,89 @@ class TrainEngine:
             self.update(lr)
 
     # ---- software pipelining across minibatches ---------------------------------------------
+    # Three stages, one frontier set each, all in flight at once:
+    #   S  sample chain of batch t+2   (integer work, latency-bound; high-priority stream)
+    #   G  layer-1 gather of batch t+1 (the HBM-bound kernel: gathers run back to back)
+    #   C  GEMMs / loss / backward / SGD of batch t  (tensor pipe + L2)
+    # so the HBM pipe never idles behind the sampler and the tensor pipe never behind the gather.
+    depth = 3
+
     def enable_pipeline(self):
-        if len(self.sets) == 1:
+        while len(self.sets) < self.depth:
             self.sets.append(_FrontierSet(self))
-            self._side = torch.cuda.Stream(device=self.dev)
+        if self._gstream is None:
+            # the side streams outrank the main stream: their short kernels must not queue behind the
+            # second wave of a 200+-CTA GEMM grid (measured: a 35 us stall per step, profiles/README.md)
+            self._gstream = torch.cuda.Stream(device=self.dev, priority=-1)
+            self._sstream = torch.cuda.Stream(device=self.dev, priority=-1)
+        self._side = self._gstream
 
-    def prime(self, b):
-        """Run the gather chain of the CURRENT set (first batch of a pipelined run)."""
-        self.enable_pipeline()
-        self._run(("prime", b, self.cur), lambda: self._gather_chain(self.sets[self.cur], b))
+    def reset_pipeline(self):
+        self.queue = []
+        self.cur = 0
 
-    def train_step_pipelined(self, b, lr, b_next=None, allreduce=None):
-        """One train step on the current set (its gather chain already done by ``prime`` or by the
-        previous call) while the sample -> gather chain of the NEXT batch -- already staged in the
-        other set -- runs concurrently on a side stream.  Afterwards the sets swap roles."""
+    def push(self, nodes, labels, step, on_device=False):
+        """Stage the next minibatch (host ids/labels, or device tensors with ``on_device``) into the
+        next free frontier set and append it to the pipeline queue."""
         self.enable_pipeline()
-        b_next = b if b_next is None else b_next
+        if len(self.queue) >= self.depth:
+            raise RuntimeError("pipeline queue is full (%d batches in flight)" % self.depth)
+        slot = (self.cur + len(self.queue)) % self.depth
+        b = (self.stage_device if on_device else self.stage)(nodes, labels, step, slot=slot)
+        self.queue.append({"slot": slot, "b": b, "state": 0,
+                           "ids": None if on_device else np.array(nodes, dtype=np.int64, copy=True)})
+        return b
+
+    def step_pipelined(self, lr, allreduce=None):
+        """Train on the oldest queued batch while the next one is gathered and the one after is
+        sampled.  Stages a batch has not been through yet (start of a run) are caught up first."""
+        q = self.queue
+        if not q:
+            raise RuntimeError("step_pipelined: no batch queued (call push first)")
         p = self.cur
+        assert q[0]["slot"] == p
+        if q[0]["state"] < 1:
+            self._run(("s", q[0]["b"], p), lambda: self._sample_chain(self.sets[p], q[0]["b"]))
+            q[0]["state"] = 1
+        if q[0]["state"] < 2:
+            self._run(("g", q[0]["b"], p), lambda: self._gather(self.sets[p], q[0]["b"]))
+            q[0]["state"] = 2
+        if len(q) > 1 and q[1]["state"] < 1:
+            s1 = q[1]["slot"]
+            self._run(("s", q[1]["b"], s1), lambda: self._sample_chain(self.sets[s1], q[1]["b"]))
+            q[1]["state"] = 1
+        b0 = q[0]["b"]
+        b1 = q[1]["b"] if len(q) > 1 else None
+        b2 = q[2]["b"] if len(q) > 2 else None
         if allreduce is None:
-            self._run(("pipe", b, b_next, float(lr), p), lambda: self._overlapped(p, b, b_next, lr))
+            self._run(("pipe", p, b0, b1, b2, float(lr)), lambda: self._overlapped(p, b0, b1, b2, lr))
         else:
             # data parallel: the NCCL all-reduce is enqueued eagerly (capturing a collective inside a
-            # forked graph deadlocked across ranks), so the two chains are separate graphs on two
-            # streams: the next batch's gather chain runs on the side stream while the main stream
-            # does compute -> all-reduce -> SGD.
+            # forked graph deadlocked across ranks), so each stage is its own graph on its own stream:
+            # gather and sample run on the side streams during compute -> all-reduce -> SGD.
             main = torch.cuda.current_stream()
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                self._run(("gchain", b_next, 1 - p), lambda: self._gather_chain(self.sets[1 - p], b_next))
-            self._run(("cchain", b, p), lambda: self._compute_chain(self.sets[p], b))
+            if b1 is not None:
+                self._gstream.wait_stream(main)
+                with torch.cuda.stream(self._gstream):
+                    self._run(("g", b1, (p + 1) % self.depth), lambda: self._gather(self.sets[(p + 1) % self.depth], b1))
+            if b2 is not None:
+                self._sstream.wait_stream(main)
+                with torch.cuda.stream(self._sstream):
+                    self._run(("s", b2, (p + 2) % self.depth),
+                              lambda: self._sample_chain(self.sets[(p + 2) % self.depth], b2))
+            self._run(("cchain", b0, p), lambda: self._compute_chain(self.sets[p], b0))
             allreduce(self.flat_g)
             self.update(lr)
-            main.wait_stream(self._side)
-        self.cur = 1 - p
+            if b1 is not None:
+                main.wait_stream(self._gstream)
+            if b2 is not None:
+                main.wait_stream(self._sstream)
+        if b1 is not None:
+            q[1]["state"] = 2
+        if b2 is not None:
+            q[2]["state"] = 1
+        q.pop(0)
+        self.cur = (p + 1) % self.depth
 
     def read_loss(self):
         self.loss_host.copy_(self.loss, non_blocking=True)

@@ -10,6 +10,9 @@ import torch
 
 
 class CSRGraph:
+    """Whole graph on one device.  ``sample`` is the interface the aggregator uses; the partitioned
+    variant (sharded.ShardedCSR) answers the same call through an all-to-all exchange."""
+
     def __init__(self, rowptr, col, device="cuda"):
         rowptr = np.ascontiguousarray(np.asarray(rowptr, dtype=np.int64))
         col = np.ascontiguousarray(np.asarray(col, dtype=np.int32))
@@ -23,6 +26,12 @@ class CSRGraph:
         self.device = torch.device(device)
         self.rowptr = torch.from_numpy(rowptr).to(self.device)
         self.col = torch.from_numpy(col if col.size else np.zeros(1, np.int32)).to(self.device)
+
+    def sample(self, ids, k, add_self=False, seed=0, step=0, tag=0, width=None):
+        """Fixed-width tile (idx [n, width], cnt [n]) of sampled neighbours of ``ids`` (int32 CUDA)."""
+        from . import ops
+        return ops.sample_csr(self.rowptr, self.col, self.num_nodes, ids, k, add_self=add_self, seed=seed,
+                              step=step, tag_head=tag, width=width)
 
     # ---- constructors ------------------------------------------------------------------
     @classmethod

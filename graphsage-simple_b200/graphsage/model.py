@@ -58,34 +58,32 @@ class SupervisedGraphSage(nn.Module):
         """The reference's timed unit (model.py:246-250: zero_grad, loss, backward, SGD step) as
         one fused call; returns the loss as a Python float (one 4-byte device->host read).
 
-        ``prefetch=(next_nodes, next_labels)`` starts the NEXT minibatch's neighbour sampling and
-        feature gather on a side stream while this one is in its GEMM/backward chain (the
-        data-loader style overlap the reference's single Python thread cannot do); pass the same
-        batch as ``nodes, labels`` of the following call."""
+        ``prefetch`` names the minibatches that FOLLOW this one -- ``(nodes, labels)`` or a list of
+        up to two such pairs -- so that their neighbour sampling and feature gather run on side
+        streams while this batch is in its GEMM/backward chain (the data-loader style overlap the
+        reference's single Python thread cannot do).  Pass the same batches, in order, as
+        ``nodes, labels`` of the following calls; results equal plain sequential steps."""
         from .engine import engine_for
         from . import sampling
-        eng = engine_for(self, max(len(nodes), len(prefetch[0]) if prefetch is not None else 0))
+        upcoming = [] if prefetch is None else ([prefetch] if isinstance(prefetch, tuple) else list(prefetch))
+        eng = engine_for(self, max([len(nodes)] + [len(u[0]) for u in upcoming]))
         if eng is None:
             raise RuntimeError("train_step needs the canonical 2-layer wiring (model.py:214-227)")
         with sampling.top_level_call() as step:
-            if prefetch is None and getattr(self, "_primed", None) is None:
+            if not upcoming and not eng.queue:
                 b = eng.stage(nodes, labels, step)
                 eng.train_step(b, lr, self.grad_allreduce)
                 return eng.read_loss()
-            primed = getattr(self, "_primed", None)
-            if primed is None or len(primed) != len(nodes) or not np.array_equal(primed, np.asarray(nodes)):
-                b = eng.stage(nodes, labels, step)          # not prefetched: do its gather chain now
-                eng.prime(b)
-            b = len(nodes)
-            if prefetch is not None:
-                eng.enable_pipeline()
-                nb = eng.stage(prefetch[0], prefetch[1], step + 1, slot=1 - eng.cur)
-                eng.train_step_pipelined(b, lr, nb, self.grad_allreduce)
-                self._primed = np.array(prefetch[0], copy=True)
-            else:                                           # last batch of a pipelined run
-                eng._run(("tail", b, eng.cur), lambda: eng._compute_chain(eng.sets[eng.cur], b))
-                if self.grad_allreduce is not None:
-                    self.grad_allreduce(eng.flat_g)
-                eng.update(lr)
-                self._primed = None
+            same = lambda entry, ids: entry["ids"] is not None and len(entry["ids"]) == len(ids) and \
+                np.array_equal(entry["ids"], np.asarray(ids, dtype=np.int64))
+            if not eng.queue or not same(eng.queue[0], nodes):
+                eng.reset_pipeline()
+                eng.push(nodes, labels, step)
+            for j, (nn, ll) in enumerate(upcoming[:eng.depth - 1]):
+                if len(eng.queue) > j + 1 and not same(eng.queue[j + 1], nn):
+                    del eng.queue[j + 1:]                    # a different batch was announced earlier
+                if len(eng.queue) <= j + 1:
+                    eng.push(nn, ll, step + 1 + j)
+            del eng.queue[len(upcoming) + 1:]
+            eng.step_pipelined(lr, self.grad_allreduce)
         return eng.read_loss()

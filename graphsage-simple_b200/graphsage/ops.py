@@ -238,6 +238,31 @@ def classifier_xent(h, wc, labels, grad_scale=1.0, logits=None, loss=None, gh=No
     return loss
 
 
+def head_supported(d1, k2_in, d2, num_classes):
+    return bool(N.load().gs_head_supported(int(d1), int(k2_in), int(d2), int(num_classes)))
+
+
+def head_ws(n, k2_in, num_classes, device):
+    """Zeroed workspace for head_fwd_bwd (holds its re-arming reduction tickets)."""
+    return torch.zeros(int(N.load().gs_head_ws_floats(int(n), int(k2_in), int(num_classes))), device=device)
+
+
+def head_fwd_bwd(h1, d1, idx, cnt, self_slots, w2, act2, wc, labels, grad_scale, comb2, h2, logits, loss,
+                 gh1, gw2, gwc, ws):
+    """Fused outer layer + classifier + loss + backward -- see gs_head_fwd_bwd."""
+    lib = N.load()
+    N.require_cuda(h1, idx, cnt, w2, wc, labels, comb2, h2, gh1, gw2, gwc, ws)
+    n, width = idx.shape
+    N.check(lib.gs_head_fwd_bwd(N.ptr(h1), h1.stride(0), int(d1), N.ptr(idx), N.ptr(cnt), width, N.ptr(self_slots),
+                                N.ptr(w2), w2.stride(0), w2.shape[0], int(act2), N.ptr(wc), wc.stride(0), wc.shape[0],
+                                N.ptr(labels), n, float(grad_scale), N.ptr(comb2), comb2.stride(0),
+                                N.ptr(h2), h2.stride(0), N.ptr(logits), logits.stride(0) if logits is not None else 0,
+                                N.ptr(loss), N.ptr(gh1), gh1.stride(0), N.ptr(gw2), gw2.stride(0),
+                                N.ptr(gwc), gwc.stride(0), N.ptr(ws), N.stream()), "gs_head_fwd_bwd")
+    LAUNCHES[0] += 2
+    return loss
+
+
 def sgd_step(p, g, lr):
     lib = N.load()
     N.require_cuda(p, g)
@@ -245,6 +270,23 @@ def sgd_step(p, g, lr):
     N.check(lib.gs_sgd_step(N.ptr(p), N.ptr(g), float(lr), p.numel(), N.stream()), "gs_sgd_step")
     LAUNCHES[0] += 1
     return p
+
+
+def bucket_by_owner(ids, world, emit_local=False):
+    """Stable counting sort of int32 ids by owner = id % world -- see gs_bucket_by_owner.
+    Returns (send_ids [n], perm [n], counts [world]) on the device."""
+    lib = N.load()
+    N.require_cuda(ids)
+    n = ids.shape[0]
+    dev = ids.device
+    scratch = torch.empty(max(lib.gs_bucket_scratch_ints(n, int(world)), 1), device=dev, dtype=torch.int32)
+    send_ids = torch.empty(max(n, 1), device=dev, dtype=torch.int32)[:n]
+    perm = torch.empty(max(n, 1), device=dev, dtype=torch.int32)[:n]
+    counts = torch.empty(int(world), device=dev, dtype=torch.int32)
+    N.check(lib.gs_bucket_by_owner(N.ptr(ids), n, None, int(world), int(bool(emit_local)), N.ptr(scratch),
+                                   N.ptr(send_ids), N.ptr(perm), N.ptr(counts), N.stream()), "gs_bucket_by_owner")
+    LAUNCHES[0] += 3 if n else 0
+    return send_ids, perm, counts
 
 
 def advance_step(step_dev):

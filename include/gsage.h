@@ -160,6 +160,30 @@ GS_API int gs_classifier_xent(const float* h, int64_t ld_h, const float* wc, int
                        float* gh, int64_t ld_gh, float* gwc, int64_t ld_gwc,
                        float* ws, void* stream);
 
+/* ---- fused head: outer layer + classifier + loss + backward, two launches ---------------------
+ * For the outer (last) layer of the 2-layer model, whose input rows are the previous layer's
+ * outputs h1 (positions, not node ids): replaces aggregators.py:54-74 (mean over the sampled
+ * tile), encoders.py:49-61 (self | neigh concat, W2 GEMM, activation), model.py:57-69 (classifier,
+ * mean cross-entropy) and their autograd backward (model.py:249) for n targets at once:
+ *   comb2[i] = [h1[self_slots[i]] | mean_j h1[idx[i,j]]]   (no self half if self_slots == NULL)
+ *   h2 = act2(comb2 . w2^T);  logits = h2 . wc^T;  loss[0] = mean CE(logits, labels)
+ *   gw2, gwc = weight gradients (overwritten; deterministic two-stage reduction)
+ *   gh1 += d loss / d h1   (128-bit reductions into a caller-zeroed [*, d1] buffer)
+ * with every gradient scaled by grad_scale.  Supported shapes: gs_head_supported() (d1 == d2 ==
+ * 128, num_classes <= 128).  ws: gs_head_ws_floats() floats, 16-B aligned, ZEROED ONCE by the
+ * caller before first use (it holds re-arming tickets).  logits may be NULL.                 */
+GS_API int gs_head_supported(int32_t d1, int32_t k2_in, int32_t d2, int32_t num_classes);
+GS_API int64_t gs_head_ws_floats(int32_t n, int32_t k2_in, int32_t num_classes);
+GS_API int gs_head_fwd_bwd(const float* h1, int64_t ld_h1, int32_t d1,
+                    const int32_t* idx, const int32_t* cnt, int32_t width, const int32_t* self_slots,
+                    const float* w2, int64_t ld_w2, int32_t d2, int32_t act2,
+                    const float* wc, int64_t ld_wc, int32_t num_classes,
+                    const int64_t* labels, int32_t n, float grad_scale,
+                    float* comb2, int64_t ld_comb2, float* h2, int64_t ld_h2,
+                    float* logits, int64_t ld_logits, float* loss,
+                    float* gh1, int64_t ld_gh1, float* gw2, int64_t ld_gw2, float* gwc, int64_t ld_gwc,
+                    float* ws, void* stream);
+
 /* ---- K6: SGD -----------------------------------------------------------------------------
  * Replaces torch.optim.SGD(lr=0.7).step(), graphsage/model.py:237, 250: p -= lr * g.      */
 GS_API int gs_sgd_step(float* p, const float* g, float lr, int64_t n, void* stream);
@@ -169,6 +193,18 @@ GS_API int gs_sgd_step(float* p, const float* g, float lr, int64_t n, void* stre
 GS_API int gs_gather_rows(const float* table, int64_t ld_table, int32_t dim, const int32_t* ids,
                    int32_t n_max, const int32_t* n_dev, float* out, int64_t ld_out,
                    void* stream);
+
+/* ---- partitioned table / CSR: bucket ids by owner ---------------------------------------------
+ * No reference counterpart (the reference is single-process); this is the first step of the
+ * exchange that replaces the local lookups `features(LongTensor(unique_nodes_list))`
+ * (aggregators.py:62-65) and `adj_lists[int(node)]` (encoders.py:47) when rows are partitioned
+ * by owner = id % world.  Stable counting sort of ids[0..n) by owner:
+ *   send_ids[pos] = ids[i] (or ids[i] / world if emit_local), perm[i] = pos, counts[o] = |bucket o|
+ * with bucket o occupying send_ids[sum(counts[:o]) ...).  scratch: gs_bucket_scratch_ints ints.  */
+GS_API int32_t gs_bucket_scratch_ints(int32_t n_max, int32_t world);
+GS_API int gs_bucket_by_owner(const int32_t* ids, int32_t n_max, const int32_t* n_dev, int32_t world,
+                       int32_t emit_local, int32_t* scratch, int32_t* send_ids, int32_t* perm,
+                       int32_t* counts, void* stream);
 
 /* Small device-side helpers used to keep a training step free of host round trips.       */
 GS_API int gs_advance_step(int64_t* step_dev, void* stream);                    /* ++*step_dev   */

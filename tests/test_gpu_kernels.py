@@ -305,3 +305,75 @@ def test_encoder_tensor_core_device_row_count(ops):
     ops.encoder_wgrad_tc(x, h, gh, 1, gw, n_dev=n_dev)
     dz = gh[:n].double() * (ref > 0)
     assert relerr(gw.cpu().numpy(), (dz.t() @ x[:n].double()).cpu().numpy()) < REL
+
+
+@pytest.mark.parametrize("n,sage,c,act,width", [(1024, True, 41, 1, 25), (37, True, 7, 2, 10), (300, False, 128, 1, 5),
+                                                (8, False, 3, 1, 1), (513, True, 47, 1, 26)])
+def test_fused_head_matches_fp64_reference(ops, n, sage, c, act, width):
+    """gs_head_fwd_bwd (outer layer + classifier + loss + backward in two launches) against an fp64
+    torch restatement of aggregators.py:54-74, encoders.py:49-61, model.py:57-69 and autograd."""
+    rng = np.random.default_rng(11)
+    d1 = d2 = 128
+    k2 = 2 * d1 if sage else d1
+    m = n + 3 * n + 5                                   # rows of h1: [targets | hop-1 slots]
+    h1 = rng.standard_normal((m, d1)).astype(np.float32)
+    cnt = rng.integers(0, width + 1, n).astype(np.int32)
+    cnt[0] = width
+    idx = np.full((n, width), -1, dtype=np.int32)
+    for i in range(n):                                  # first half of the targets share hub slot n
+        if cnt[i] and i < n // 2:
+            idx[i, :cnt[i]] = np.concatenate([[n], np.sort(rng.choice(np.arange(n + 1, m), cnt[i] - 1, replace=False))])
+        else:
+            idx[i, :cnt[i]] = np.sort(rng.choice(np.arange(n, m), cnt[i], replace=False))
+    w2 = (rng.standard_normal((d2, k2)) / np.sqrt(k2)).astype(np.float32)
+    wc = (rng.standard_normal((c, d2)) / np.sqrt(d2)).astype(np.float32)
+    labels = rng.integers(0, c, n).astype(np.int64)
+    scale = 0.75
+    assert ops.head_supported(d1, k2, d2, c)
+    dv = lambda a: dev(a)
+    comb2 = torch.zeros((n, k2), device="cuda"); h2 = torch.zeros((n, d2), device="cuda")
+    logits = ops.empty_rows(n, c, "cuda", zero=True); loss = torch.zeros(1, device="cuda")
+    gh1 = torch.zeros((m, d1), device="cuda"); gw2 = torch.zeros((d2, k2), device="cuda")
+    gwc = ops.empty_rows(c, d2, "cuda", zero=True)
+    ws = ops.head_ws(n, k2, c, "cuda")
+    self_slots = dv(np.arange(n, dtype=np.int32)) if sage else None
+    for rep in range(2):                                # second call: re-armed tickets, gh1 re-zeroed
+        gh1.zero_()
+        ops.head_fwd_bwd(dv(h1), d1, dv(idx), dv(cnt), self_slots, dv(w2), act, dv(wc), dv(labels), scale,
+                         comb2, h2, logits, loss, gh1, gw2, gwc, ws)
+    # fp64 reference
+    H1 = torch.tensor(h1, dtype=torch.float64, requires_grad=True)
+    W2 = torch.tensor(w2, dtype=torch.float64, requires_grad=True)
+    WC = torch.tensor(wc, dtype=torch.float64, requires_grad=True)
+    mask = torch.zeros((n, m), dtype=torch.float64)
+    for i in range(n):
+        mask[i, idx[i, :cnt[i]]] = 1.0
+    mean = (mask / mask.sum(1, keepdim=True).clamp(min=1)).mm(H1)
+    comb = torch.cat([H1[:n], mean], 1) if sage else mean
+    z = comb.mm(W2.t())
+    hh = torch.relu(z) if act == 1 else torch.sigmoid(z)
+    sc = hh.mm(WC.t())
+    ref = torch.nn.functional.cross_entropy(sc, torch.tensor(labels)) * scale
+    ref.backward()
+    assert abs(float(loss.item()) * scale - float(ref)) / abs(float(ref)) < REL
+    assert relerr(comb2.cpu().numpy(), comb.detach().numpy()) < REL
+    assert relerr(h2.cpu().numpy(), hh.detach().numpy()) < REL
+    assert relerr(logits.cpu().numpy(), sc.detach().numpy()) < REL
+    assert relerr(gwc.cpu().numpy(), WC.grad.numpy()) < REL
+    assert relerr(gw2.cpu().numpy(), W2.grad.numpy()) < REL
+    assert relerr(gh1.cpu().numpy(), H1.grad.numpy()) < REL
+
+
+@pytest.mark.parametrize("n,world,local", [(100000, 8, True), (1023, 2, False), (1025, 3, True), (1, 4, False), (5000, 1, True),
+                                           (4096, 16, False)])
+def test_bucket_by_owner_bit_exact(ops, n, world, local):
+    """gs_bucket_by_owner == stable sort of the ids by (id % world)."""
+    rng = np.random.default_rng(n + world)
+    ids = rng.integers(0, 2_400_000, n).astype(np.int32)
+    send, perm, counts = ops.bucket_by_owner(dev(ids), world, emit_local=local)
+    order = np.argsort(ids % world, kind="stable")
+    want = ids[order] // world if local else ids[order]
+    assert np.array_equal(counts.cpu().numpy(), np.bincount(ids % world, minlength=world))
+    assert np.array_equal(send.cpu().numpy(), want)
+    inv = np.empty(n, dtype=np.int64); inv[order] = np.arange(n)
+    assert np.array_equal(perm.cpu().numpy(), inv)

@@ -297,3 +297,46 @@ def test_pipelined_prefetch_equals_sequential_steps(golden, gcn):
     for a, b in zip(out["seq"][1], out["pipe"][1]):
         assert relerr(b, a) < REL
     assert out["seq"][0][0] != out["seq"][0][-1]
+
+
+@pytest.mark.parametrize("gcn,feat,batch", [(False, 64, 96), (True, 36, 33), (False, 602, 256)])
+def test_fused_engine_wide_layers_equal_op_by_op_path(gcn, feat, batch):
+    """Hidden width 128/128 (the BASELINE configs): the engine takes the tcgen05 layer-1 GEMMs and the
+    fused head (gs_head_fwd_bwd); loss, the three gradients and the SGD update must equal the
+    op-by-op autograd path (fp32 SIMT kernels) on the same device-drawn samples."""
+    from graphsage import sampling
+    rng = np.random.default_rng(5)
+    n, c, k1, k2 = 1500, 41, 5, 7
+    src, dst = rng.integers(0, n, (2, 6 * n))
+    ring = np.arange(n)
+    adj = {v: set() for v in range(n)}
+    for a, b in zip(np.concatenate([src, ring]), np.concatenate([dst, (ring + 1) % n])):
+        adj[int(a)].add(int(b)); adj[int(b)].add(int(a))
+    g = {"table": rng.standard_normal((n, feat)).astype(np.float32),
+         "w1": (rng.standard_normal((128, feat if gcn else 2 * feat)) / np.sqrt(feat)).astype(np.float32),
+         "w2": (rng.standard_normal((128, 128 if gcn else 256)) / 16).astype(np.float32),
+         "wc": (rng.standard_normal((c, 128)) / 11).astype(np.float32)}
+    labels_all = rng.integers(0, c, (n, 1)).astype(np.int64)
+    batches = [rng.permutation(n)[:batch] for _ in range(4)]
+    res = {}
+    for mode in ("ops", "engine"):
+        model, enc1, enc2 = build_model(g, gcn, adj, adj, k1, k2)
+        model.use_engine = False if mode == "ops" else None
+        sampling.seed(31)
+        opt = torch.optim.SGD(model.parameters(), lr=0.3)
+        out = []
+        for nodes in batches:
+            opt.zero_grad()
+            loss = model.loss(list(nodes), torch.LongTensor(labels_all[nodes]))
+            loss.backward()
+            out.append((loss.item(), model.weight.grad.clone(), enc2.weight.grad.clone(), enc1.weight.grad.clone()))
+            opt.step()
+        out.append((0.0, model.weight.detach().clone(), enc2.weight.detach().clone(), enc1.weight.detach().clone()))
+        res[mode] = out
+        if mode == "engine":
+            eng = model._engine
+            assert eng.head and eng.tc1 == (enc1.weight.shape[1] % 4 == 0 and enc1.weight.shape[1] >= 32)
+    for a, b in zip(res["ops"], res["engine"]):
+        assert abs(a[0] - b[0]) <= REL * max(abs(a[0]), 1e-30)
+        for x, y in zip(a[1:], b[1:]):
+            assert relerr(y.cpu().numpy(), x.cpu().numpy()) < REL
