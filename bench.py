@@ -50,6 +50,9 @@ def parse():
                     help="SGD lr (reference uses 0.7; 0.01 keeps long runs on random labels finite)")
     ap.add_argument("--cpu-batch", type=int, default=256, help="targets per step of the CPU baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--workload", default="reddit", choices=["reddit", "products"],
+                    help="reddit: BASELINE config 4 (default, the judged line); products: config 5 -- 3-layer model, "
+                         "feature table + CSR partitioned over the ranks, NCCL all-to-all per lookup")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
     return ap.parse_args()
@@ -185,7 +188,8 @@ def workload_config(args, batch):
                         "%d (hop-1), SGD" % (args.nodes, args.pairs, args.feat, args.classes, args.hidden,
                                             args.hidden, args.k2, args.k1),
             "batch_per_gpu": batch, "global_batch": batch * max(args.gpus, 1),
-            "parallelism": "dp%d (graph + features replicated, NCCL all-reduce of weight grads)" % args.gpus,
+            "parallelism": "dp%d (graph + features replicated, all-reduce of weight grads: %s)" % (
+                args.gpus, getattr(args, "dp_mode", "none")),
             "l2_policy": "inputs larger than L2: 561 MB feature table, fresh random targets every step",
             "lr": args.lr}
 
@@ -239,12 +243,28 @@ def run_b200(args):
     assert eng is not None, "canonical wiring not recognised"
     allreduce = None
     lr = args.lr
+    dp_mode = "none"
     if world > 1:
         from graphsage import dist as gdist
-        allreduce = gdist.make_allreduce()
         lr = gdist.dp_lr(args.lr, world)   # mean over the global batch = sum of rank means / world
         eng.grad_scale = gdist.local_grad_scale(B, B * world, world)
+        dp_mode = os.environ.get("GSAGE_DP", "peer")
+        if dp_mode == "peer":
+            # all-reduce fused into the SGD kernel over NVLink peer memory: stays inside the step's CUDA graph
+            try:
+                eng.peer = gdist.PeerAllreduceSGD(eng.flat_w.numel(), dev)
+            except Exception as e:            # no symmetric-memory support on this box: NCCL between graphs
+                print("peer all-reduce unavailable (%s); falling back to NCCL" % str(e).splitlines()[0], file=sys.stderr)
+                dp_mode = "nccl"
+        ok = torch.tensor([1 if dp_mode == "peer" else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            dp_mode, eng.peer = "nccl", None
+        if dp_mode == "nccl":
+            allreduce = gdist.make_allreduce()
 
+    args.dp_mode = {"peer": "fused into the SGD kernel over NVLink peer memory", "nccl": "NCCL between graphs",
+                    "none": "n/a"}[dp_mode]
     # ---- (1) device-resident throughput: inputs already in HBM, one graph replay per step.
     # Steps are software-pipelined three deep: while batch i is in its GEMM/backward chain, batch
     # i+1 is in its feature gather and batch i+2 in its sampler chain on side streams (all inside
@@ -339,7 +359,9 @@ def run_b200(args):
     # ---- (4) per-kernel times (eager launches, CUDA events around each C-ABI call)
     kernels, roofline = None, None
     if rank == 0 and not args.no_kernel_profile:
+        peer, eng.peer = eng.peer, None          # rank 0 alone from here on: plain local SGD
         kernels = profile_kernels(eng, B, lr, d_nodes, d_labels)
+        eng.peer = peer
         import json as _j
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         peak, which = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
@@ -422,9 +444,140 @@ def profile_kernels(eng, B, lr, d_nodes, d_labels, iters=5):
     return {k: v / iters for k, v in totals.items()}
 
 
+# ------------------------------------------------------------------------------ config 5
+def build_partitioned_graph(n, pairs, rank, world, seed=2, chunk=1 << 24):
+    """Rows v % world == rank of the symmetrised, deduplicated random graph of SURVEY.md s8d
+    (products-shape: default_rng(2) pairs).  Every rank draws the same pair stream and keeps its rows,
+    so no rank ever materialises the whole 124 M-entry CSR."""
+    rng = np.random.default_rng(seed)
+    keys = []
+    left = pairs
+    while left > 0:
+        m = min(chunk, left)
+        e = rng.integers(0, n, (2, m), dtype=np.int64)
+        for a, b in ((e[0], e[1]), (e[1], e[0])):
+            sel = (a % world) == rank
+            keys.append(a[sel] * np.int64(n) + b[sel])
+        left -= m
+    key = np.unique(np.concatenate(keys))
+    del keys
+    s = key // n
+    col = (key - s * n).astype(np.int32)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(s, minlength=n), out=rowptr[1:])
+    return rowptr, col
+
+
+def run_products(args):
+    """BASELINE config 5: synthetic ogbn-products-shape graph, 3-layer SAGE-mean (fan-out 15/10/5 from the
+    targets outward), feature table AND CSR partitioned by owner = id % world, every lookup an NCCL
+    all-to-all round trip (graphsage/sharded.py), weight gradients all-reduced.  Op-by-op autograd path."""
+    import torch
+    import torch.distributed as dist
+    from graphsage import ops, sampling, sharded
+    from graphsage.model import build_sage
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.nodes if args.nodes != 233000 else 2400000
+    pairs = args.pairs if args.pairs != 5800000 else 62000000
+    feat = args.feat if args.feat != 602 else 100
+    classes = args.classes if args.classes != 41 else 47
+    fan = [5, 10, 15]                                    # innermost first
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    t0 = time.perf_counter()
+    rowptr, col = build_partitioned_graph(n, pairs, rank, world)
+    deg_max = torch.tensor([int(np.diff(rowptr).max())], device=dev)
+    if world > 1:
+        dist.all_reduce(deg_max, op=dist.ReduceOp.MAX)
+    ex = sharded.OwnerExchange(rank, world)
+    graph = sharded.ShardedCSR(rowptr, col, n, int(deg_max.item()), ex, dev)
+    entries_local = int(col.shape[0])
+    del rowptr, col
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2)
+    full = torch.randn(n, feat, device=dev, generator=gen)      # 0.96 GB transient; each rank keeps its rows
+    feats = sharded.ShardedFeatures(full[rank::world].contiguous(), n, exchange=ex)
+    del full
+    labels_np = np.random.default_rng(2).integers(0, classes, (n, 1)).astype(np.int64)
+    torch.manual_seed(2)
+    model, encs = build_sage(feats, feat, [args.hidden] * 3, graph, fan, classes)
+    sampling.seed(2)
+    build_s = time.perf_counter() - t0
+    opt = torch.optim.SGD(model.parameters(), lr=args.lr)
+    rng = np.random.default_rng(200 + rank)
+    params = list(model.parameters())
+
+    def step():
+        nodes = rng.integers(0, n, B)
+        opt.zero_grad()
+        loss = model.loss(nodes, labels_np[nodes])
+        loss.backward()
+        sharded.allreduce_grads(params, world, B, B * world)
+        opt.step()
+        return loss
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    sent0, launches0 = ex.bytes_sent, ops.LAUNCHES[0]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(K):
+        loss = step()
+        loss_host = loss.item()                                 # D2H read of the step's result
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks.stop_flag = True
+    clocks.join()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * K / (ms_total / 1e3)
+    sent = (ex.bytes_sent - sent0) / K
+    if rank == 0:
+        wire = sent / (ms_total / K * 1e-3) / 1e9
+        line = {"metric": METRIC.replace("2-layer", "3-layer"), "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "synthetic ogbn-products-shape graph: %d nodes, %d undirected pairs (CSR ~2x), "
+                                       "%d-d fp32 features, %d classes, 3-layer SAGE-mean concat, hidden %d, fan-out "
+                                       "15/10/5 from the targets outward, SGD" % (n, pairs, feat, classes, args.hidden),
+                           "batch_per_gpu": B, "global_batch": B * world,
+                           "parallelism": "feature table + CSR partitioned by owner = id %% %d; NCCL all-to-all per lookup; "
+                                          "all-reduce of weight grads" % world,
+                           "l2_policy": "inputs larger than L2: fresh random targets every step", "lr": args.lr,
+                           "csr_entries_rank0": entries_local, "build_s": build_s},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 4,
+                        "api": "the reference's loop (model.py:245-250) on the drop-in modules with host ids/labels"},
+                "gpu_launches": ops.LAUNCHES[0] - launches0, "clocks": clocks.summary(),
+                "roofline": {"kernel": "all-to-all exchange (ids + feature rows + sampled tiles), rank 0 send side",
+                             "bound": "nvlink", "achieved": wire, "peak": 900.0, "unit": "GB/s", "frac": wire / 900.0,
+                             "traffic": None, "bytes_sent_per_step_rank0": sent,
+                             "note": "op-by-op path: the step is launch/sync-bound, not wire-bound (one host sync per lookup)"},
+                "cpu_baseline": None, "loss": loss_host}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "products":
+        run_products(a)
     else:
         run_b200(a)

@@ -121,10 +121,11 @@ extern "C" int32_t gs_bucket_scratch_ints(int32_t n_max, int32_t world) {
 extern "C" int gs_bucket_by_owner(const int32_t* ids, int32_t n_max, const int32_t* n_dev, int32_t world,
                                   int32_t emit_local, int32_t* scratch, int32_t* send_ids, int32_t* perm,
                                   int32_t* counts, void* stream) {
-    if (!ids || !scratch || !send_ids || !perm || !counts || n_max < 0) return GS_EINVAL;
+    if (!counts || n_max < 0) return GS_EINVAL;
     if (world < 1 || world > kMaxWorld) return GS_ENOSUP;
     cudaStream_t s = (cudaStream_t)stream;
-    if (n_max == 0) {
+    if (n_max > 0 && (!ids || !scratch || !send_ids || !perm)) return GS_EINVAL;
+    if (n_max == 0) {                   // an empty request is legal (a rank may ask for nothing)
         cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * world, s);
         return e == cudaSuccess ? GS_OK : (int)e;
     }

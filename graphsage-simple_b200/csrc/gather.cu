@@ -228,6 +228,7 @@ extern "C" int gs_gather_mean_fwd(const float* table, int64_t ld_table, int32_t 
 
 extern "C" int gs_gather_rows(const float* table, int64_t ld_table, int32_t dim, const int32_t* ids,
                               int32_t n_max, const int32_t* n_dev, float* out, int64_t ld_out, void* stream) {
+    if (n_max == 0) return GS_OK;
     if (!table || !ids || !out || dim <= 0 || n_max < 0) return GS_EINVAL;
     if (!gs_aligned16(table) || !gs_aligned16(out) || (ld_table & 3) || (ld_out & 3)) return GS_EALIGN;
     if (ld_table < dim || ld_out < dim) return GS_EINVAL;

@@ -287,6 +287,7 @@ extern "C" int gs_sample_csr(const int64_t* rowptr, const int32_t* col, int32_t 
                              uint32_t tag_head, uint32_t tag_tail, int32_t n_head,
                              int32_t* idx, int32_t* cnt, void* stream) {
     (void)num_nodes;
+    if (n_max == 0) return GS_OK;       // empty frontier (e.g. nothing requested from this owner)
     if (!rowptr || !col || !nodes || !idx || !cnt || n_max < 0 || width <= 0) return GS_EINVAL;
     if (k > kMaxK) return GS_ENOSUP;
     if (k >= 0 && width < k + (add_self ? 1 : 0)) return GS_EINVAL;

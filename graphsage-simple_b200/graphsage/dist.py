@@ -46,3 +46,36 @@ def sgd_from_summed(params, flat_sum, lr, world):
             k = p.numel()
             p.add_(flat_sum[off:off + k].view_as(p), alpha=-dp_lr(lr, world))
             off += k
+
+
+class PeerAllreduceSGD:
+    """Gradient all-reduce fused with the SGD update over NVLink peer memory (gs_allreduce_sgd): one
+    kernel per step, no NCCL call and no host synchronisation, so it sits inside the step's CUDA graph.
+    The staging buffer and flag pad live in symmetric memory (torch.distributed._symmetric_memory:
+    one allocation per rank, mapped into every peer of the box)."""
+
+    def __init__(self, n_floats, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _native as N
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n = int(n_floats)
+        assert self.n % 4 == 0
+        blocks = N.load().gs_allreduce_sgd_blocks(self.n)
+        flag_words = self.world * blocks
+        total = 2 * self.n + (flag_words + 3) // 4 * 4
+        self.buf = symm.empty(total, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.stage_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.flag_ptrs = torch.tensor([p + 4 * 2 * self.n for p in ptrs], dtype=torch.int64, device=device)
+        self.state = torch.zeros(2, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                      # every pad is zero before the first remote flag lands
+
+    def step(self, flat_w, flat_g, lr):
+        """flat_w -= lr * sum_r flat_g_r   (pass lr / world for the global-batch mean, see dp_lr)."""
+        from . import ops
+        assert flat_w.numel() == self.n and flat_g.numel() == self.n
+        return ops.allreduce_sgd(flat_w, flat_g, lr, self.stage_ptrs, self.flag_ptrs, self.rank, self.world, self.state)

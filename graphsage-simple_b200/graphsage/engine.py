@@ -239,8 +239,13 @@ class TrainEngine:
         self._gather_chain(fs, b)
         self._compute_chain(fs, b)
 
+    peer = None        # dist.PeerAllreduceSGD: data parallel with the all-reduce fused into the update kernel
+
     def _update(self, lr):
-        ops.sgd_step(self.flat_w, self.flat_g, lr)
+        if self.peer is not None:
+            self.peer.step(self.flat_w, self.flat_g, lr)
+        else:
+            ops.sgd_step(self.flat_w, self.flat_g, lr)
 
     def _overlapped(self, p, b0, b1, b2, lr):
         """One pipelined step as a fork/join over three streams (captured as ONE CUDA graph):
@@ -485,6 +490,9 @@ def engine_for(model, batch):
         return None
     if enc1.initializer in TABLE_INITIALIZERS or enc2.initializer in TABLE_INITIALIZERS:
         return None
+    from .graph import CSRGraph
+    if not (isinstance(enc1.graph, CSRGraph) and isinstance(enc2.graph, CSRGraph)):
+        return None                      # partitioned graph (sharded.ShardedCSR): op-by-op path
     if not (_closure_reaches(enc2.features, enc1) and _closure_reaches(agg2.features, enc1)):
         return None
     if enc1.gcn != enc2.gcn or getattr(enc1, "base_model", None) is not None:

@@ -14,6 +14,35 @@ from .aggregators import _device
 from .functional import EncoderGemm, SoftmaxXent
 
 
+def build_sage(features, feat_dim, hidden, adj_lists, fanouts, num_classes, gcn=False, agg_gcn=False,
+               initializer="None", feature_dim=100, num_nodes=100):
+    """Wire an L-layer supervised GraphSAGE exactly the way the reference's driver does for two
+    layers (model.py:218-227): layer l's ``features`` is the closure ``lambda nodes: enc_{l-1}(nodes).t()``.
+
+    hidden   -- output width per layer, innermost first (model.py:219, 221: [identity_dim, 128])
+    fanouts  -- ``num_sample`` per layer, innermost first (the reference's nominal (num_sample1,
+                num_sample2), model.py:188-189, which its driver sets on an attribute nobody reads)
+    adj_lists-- mapping int -> set (model.py:303-310), a CSRGraph, or a sharded.ShardedCSR
+    Returns (SupervisedGraphSage, [enc_1 .. enc_L])."""
+    from .aggregators import MeanAggregator
+    from .encoders import Encoder
+    encs = []
+    prev_feats, prev_dim = features, feat_dim
+    for layer, (dim, k) in enumerate(zip(hidden, fanouts)):
+        if layer == 0:
+            agg = MeanAggregator(prev_feats, initializer, cuda=True, gcn=agg_gcn, feature_dim=feature_dim,
+                                 num_nodes=num_nodes)
+            enc = Encoder(prev_feats, prev_dim, dim, adj_lists, agg, num_sample=k, initializer=initializer, gcn=gcn,
+                          cuda=True)
+        else:
+            below = encs[-1]
+            feats = (lambda b: (lambda nodes: b(nodes).t()))(below)          # model.py:220-221
+            agg = MeanAggregator(feats, cuda=True, gcn=agg_gcn)
+            enc = Encoder(feats, below.embed_dim, dim, adj_lists, agg, num_sample=k, base_model=below, gcn=gcn, cuda=True)
+        encs.append(enc)
+    return SupervisedGraphSage(num_classes, encs[-1]), encs
+
+
 class SupervisedGraphSage(nn.Module):
 
     def __init__(self, num_classes, enc):

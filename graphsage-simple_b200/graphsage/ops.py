@@ -289,6 +289,16 @@ def bucket_by_owner(ids, world, emit_local=False):
     return send_ids, perm, counts
 
 
+def allreduce_sgd(p, g, lr, stage_ptrs, flag_ptrs, rank, world, state):
+    """p -= lr * sum over ranks of g, through peer-mapped staging buffers -- see gs_allreduce_sgd."""
+    lib = N.load()
+    N.require_cuda(p, g, stage_ptrs, flag_ptrs, state)
+    N.check(lib.gs_allreduce_sgd(N.ptr(p), N.ptr(g), p.numel(), float(lr), N.ptr(stage_ptrs), N.ptr(flag_ptrs),
+                                 int(rank), int(world), N.ptr(state), N.stream()), "gs_allreduce_sgd")
+    LAUNCHES[0] += 1
+    return p
+
+
 def advance_step(step_dev):
     N.check(N.load().gs_advance_step(N.ptr(step_dev), N.stream()), "gs_advance_step")
     LAUNCHES[0] += 1

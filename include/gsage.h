@@ -188,6 +188,19 @@ GS_API int gs_head_fwd_bwd(const float* h1, int64_t ld_h1, int32_t d1,
  * Replaces torch.optim.SGD(lr=0.7).step(), graphsage/model.py:237, 250: p -= lr * g.      */
 GS_API int gs_sgd_step(float* p, const float* g, float lr, int64_t n, void* stream);
 
+/* ---- data parallel: gradient all-reduce fused with SGD over NVLink peer memory -----------------
+ * Replaces `optimizer.step()` (model.py:237, 250) when the global batch is split over `world`
+ * ranks:  p -= lr * sum_r g_r, the sum taken in rank order (identical bits on every rank).
+ * stage_ptrs / flag_ptrs: DEVICE arrays of `world` pointers, entry q = rank q's staging buffer
+ * (2 * n floats, double-buffered) / flag pad (world * gs_allreduce_sgd_blocks(n) uint32, zeroed
+ * once) as mapped into THIS process (CUDA IPC / symmetric memory).  state: 2 zeroed uint32 in
+ * local device memory (epoch, ticket).  n % 4 == 0.  Every rank must launch it once per step;
+ * no host or NCCL synchronisation is involved, so the launch can sit in a captured graph.      */
+GS_API int32_t gs_allreduce_sgd_blocks(int64_t n);
+GS_API int gs_allreduce_sgd(float* p, const float* g, int64_t n, float lr,
+                     float* const* stage_ptrs, uint32_t* const* flag_ptrs,
+                     int32_t rank, int32_t world, uint32_t* state, void* stream);
+
 /* Row gather without the mean (feature lookup aggregators.py:63-65 as a bit-exact copy):
  * out[i, 0:dim] = table[ids[i], 0:dim].                                                  */
 GS_API int gs_gather_rows(const float* table, int64_t ld_table, int32_t dim, const int32_t* ids,

@@ -23,4 +23,7 @@ Contents
                    the sampler is bit-exact against this port and property-checked
                    against the reference's semantics (take-all when deg<k, k distinct
                    members when deg>=k, uniform marginals).
+  exchange_port.py CPU restatement of OUR owner-bucketing specification for the partitioned
+                   feature table / CSR (gs_bucket_by_owner); the reference has no
+                   distributed code, so the pin is the identity "exchange == table[ids]".
 """
