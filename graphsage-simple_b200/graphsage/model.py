@@ -116,3 +116,124 @@ class SupervisedGraphSage(nn.Module):
             del eng.queue[len(upcoming) + 1:]
             eng.step_pipelined(lr, self.grad_allreduce)
         return eng.read_loss()
+
+
+# ------------------------------------------------------------------------------------------------
+# Driver: the drop-in for ``python -m graphsage.model`` (graphsage/model.py:184-259, 539-567)
+# ------------------------------------------------------------------------------------------------
+def run_model(dataset, initializer, seed, epochs, classify="node", batch_size=128, feature_dim=100, identity_dim=50,
+              data_root=".", num_samples=None, as_run=False, lr=0.7, gcn=True, data=None, verbose=True):
+    """Train + validate a 2-layer supervised GraphSAGE on cora / citeseer / pubmed: same flow, same
+    constants and same printed lines as the reference's ``run_model`` (model.py:184-259).
+
+    The reference's driver has three accidents which are NOT reproduced by default:
+    it sets ``enc.num_samples`` (an attribute nobody reads, model.py:223-224) so the effective fan-out is
+    the constructor default 10/10; it slices ``train[batch:max(train_num, batch+batch_size)]``
+    (model.py:244), so every "batch" is the rest of the epoch; and for initialisers whose table width
+    differs from ``feature_dim`` (pagerank, deepwalk) the weight shape does not match.  Here the nominal
+    per-dataset fan-outs (model.py:188-189) are applied to ``num_sample``, batches are
+    ``train[batch:batch+batch_size]``, and the table width is taken from the table.  ``as_run=True``
+    restores the reference's EFFECTIVE behaviour (fan-out 10/10, rest-of-epoch batches) for like-for-like
+    F1 / timing comparisons.  Extra arguments: ``data_root`` (the reference reads from the CWD),
+    ``num_samples=(inner, outer)``, ``lr``, ``gcn`` (the reference hard-codes gcn=True encoders),
+    ``data=(feat_data, labels, adj_lists)`` to skip the loader.  Returns a dict with the numbers printed."""
+    import random
+    import time
+    from . import data as D, sampling
+    from .engine import engine_for
+    spec = D.DATASETS[dataset]
+    np.random.seed(seed)                                                     # model.py:192-193
+    random.seed(seed)
+    sampling.seed(seed)                                                      # the device sampler's stream
+    num_nodes, num_classes = spec["num_nodes"], spec["num_classes"]
+    feat_data, labels, adj_lists = data if data is not None else D.load_dataset(dataset, feature_dim, initializer, data_root)
+    num_nodes = feat_data.shape[0]
+    if initializer != "None":
+        feature_dim = feat_data.shape[1]                                     # model.py:209-212, for every table
+    else:
+        feature_dim = feat_data.shape[1] if data is not None else spec["attr_dim"]
+    if verbose:
+        print("feature dim is", feature_dim)
+    dev = _device()
+    features = nn.Embedding(num_nodes, feature_dim, device="meta")
+    table = ops.empty_rows(num_nodes, feature_dim, dev, zero=True)
+    table.copy_(torch.from_numpy(np.asarray(feat_data, dtype=np.float32)))
+    features.weight = nn.Parameter(table, requires_grad=False)               # model.py:214-215
+    k1, k2 = (10, 10) if as_run else (num_samples if num_samples is not None else spec["num_samples"])
+    model, (enc1, enc2) = build_sage(features, feature_dim, [identity_dim, 128], adj_lists, [k1, k2], num_classes,
+                                     gcn=gcn, initializer=initializer, feature_dim=feature_dim, num_nodes=num_nodes)
+    rand_indices = np.random.permutation(num_nodes)                          # model.py:229-235
+    test_end, val_end = int(0.1 * num_nodes), int(0.2 * num_nodes)
+    test, val, train = rand_indices[:test_end], rand_indices[test_end:val_end], list(rand_indices[val_end:])
+    train_num = len(train)
+    fused = engine_for(model, min(batch_size, train_num) if not as_run else train_num) is not None
+    optimizer = None if fused else torch.optim.SGD(filter(lambda p: p.requires_grad, model.parameters()), lr=lr)
+    times, losses = [], []
+    for epoch in range(epochs):
+        random.shuffle(train)                                                # model.py:242
+        for batch in range(0, train_num, batch_size):
+            stop = max(train_num, batch + batch_size) if as_run else batch + batch_size
+            batch_nodes = train[batch:stop]
+            batch_labels = labels[np.array(batch_nodes)]
+            torch.cuda.synchronize()
+            start = time.time()
+            if fused:                                                        # zero_grad + loss + backward + step, fused
+                loss = model.train_step(batch_nodes, batch_labels, lr=lr)
+            else:                                                            # model.py:246-250 verbatim
+                optimizer.zero_grad()
+                loss_t = model.loss(batch_nodes, torch.LongTensor(batch_labels))
+                loss_t.backward()
+                optimizer.step()
+                loss = loss_t.item()
+            torch.cuda.synchronize()
+            times.append(time.time() - start)
+            losses.append(loss)
+    from sklearn.metrics import f1_score
+    val_output = model.forward(val)                                          # model.py:256
+    pred = val_output.detach().cpu().numpy().argmax(axis=1)
+    out = {"f1_micro": f1_score(labels[val], pred, average="micro"), "f1_macro": f1_score(labels[val], pred, average="macro"),
+           "avg_batch_time": float(np.mean(times)) if times else 0.0, "losses": losses, "fused_engine": fused,
+           "num_sample": (k1, k2), "test_nodes": test, "model": model}
+    if verbose:
+        print("Validation F1 micro:", out["f1_micro"])
+        print("Validation F1 macro:", out["f1_macro"])
+        print("Average batch time:", out["avg_batch_time"])
+    return out
+
+
+def main(argv=None):
+    """Same flags as the reference's CLI (model.py:539-567) plus the knobs run_model adds."""
+    import argparse
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--initializer", type=str, default="None", help="node feature initialiation method")
+    parser.add_argument("--identity_dim", type=int, default=50, help="node embedding dimension")
+    parser.add_argument("--feature_dim", type=int, default=100, help="node feature dimension")
+    parser.add_argument("--seed", type=int, default=1, help="random seed for initialization")
+    parser.add_argument("--epochs", type=int, default=5, help="number of epochs")
+    parser.add_argument("--dataset", type=str, default="cora", help="dataset used")
+    parser.add_argument("--classify", type=str, default="node", help="classify task")
+    parser.add_argument("--batch_size", type=int, default=128)
+    parser.add_argument("--data_root", type=str, default=".", help="directory holding cora/, citeseer/, pubmed-data/")
+    parser.add_argument("--num_sample1", type=int, default=None, help="fan-out of the inner layer")
+    parser.add_argument("--num_sample2", type=int, default=None, help="fan-out of the outer layer")
+    parser.add_argument("--lr", type=float, default=0.7)
+    parser.add_argument("--as_run", action="store_true",
+                        help="reproduce the reference driver's effective behaviour (fan-out 10/10, rest-of-epoch batches)")
+    parser.add_argument("--synthetic", action="store_true",
+                        help="write a synthetic dataset in the reference's file formats into --data_root first")
+    args = parser.parse_args(argv)
+    if args.synthetic:
+        from . import data as D
+        D.write_synthetic_dataset(args.dataset, args.data_root, seed=args.seed)
+    ns = None
+    if args.num_sample1 is not None or args.num_sample2 is not None:
+        from . import data as D
+        d1, d2 = D.DATASETS[args.dataset]["num_samples"]
+        ns = (args.num_sample1 or d1, args.num_sample2 or d2)
+    return run_model(args.dataset, args.initializer, args.seed, args.epochs, classify=args.classify,
+                     batch_size=args.batch_size, feature_dim=args.feature_dim, identity_dim=args.identity_dim,
+                     data_root=args.data_root, num_samples=ns, as_run=args.as_run, lr=args.lr)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+"""End-to-end driver parity (north_star: "Cora/Pubmed validation F1 must match within
+run-to-run noise"): graphsage.model.run_model -- the drop-in for `python -m graphsage.model`
+(reference model.py:184-259, 539-567) -- against validation F1 of the UNMODIFIED reference driver on the
+same synthetic planted-partition datasets (tests/golden/driver.json, made by
+tests/golden/make_golden_driver.py; the files are regenerated here bit-for-bit).  The device sampler
+draws from Philox, the reference from CPython's Mersenne Twister, so the comparison is statistical:
+mean F1 over seeds within max(0.05, 3 sigma) of the reference's mean."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "driver.json")
+
+
+@pytest.fixture(scope="module")
+def setup(tmp_path_factory):
+    from graphsage import data as D
+    g = json.load(open(GOLDEN))
+    root = str(tmp_path_factory.mktemp("driver_data"))
+    for ds, seed in g["data_seed"].items():
+        D.write_synthetic_dataset(ds, root, seed=seed)
+    return root, g["runs"]
+
+
+@pytest.mark.parametrize("dataset,initializer", [("cora", "None"), ("citeseer", "node_degree"), ("cora", "random_normal")])
+def test_run_model_f1_matches_reference_driver(setup, dataset, initializer):
+    import torch
+    from graphsage.model import run_model
+    root, runs = setup
+    ref = [r for r in runs if r["dataset"] == dataset and r["initializer"] == initializer]
+    assert len(ref) >= 3
+    mine = []
+    for r in ref:
+        torch.manual_seed(r["seed"])
+        out = run_model(dataset, initializer, r["seed"], r["epochs"], data_root=root, as_run=True, verbose=False)
+        assert np.isfinite(out["losses"]).all() and out["num_sample"] == (10, 10)
+        assert out["fused_engine"] == (initializer not in ("1hot", "node_degree"))
+        mine.append((out["f1_micro"], out["f1_macro"]))
+    for j, key in enumerate(("f1_micro", "f1_macro")):
+        want = np.array([r[key] for r in ref])
+        got = np.array([m[j] for m in mine])
+        tol = max(0.05, 3 * want.std())
+        assert abs(got.mean() - want.mean()) <= tol, (key, got, want)
+
+
+def test_cli_with_intended_knobs(setup, capsys):
+    """`python -m graphsage.model` flags (model.py:540-554) + the knobs the reference meant to have: nominal
+    fan-outs on num_sample, batch_size-sized batches.  Learns the planted partition."""
+    from graphsage.model import main
+    root, _ = setup
+    out = main(["--dataset", "cora", "--epochs", "3", "--seed", "4", "--data_root", root, "--identity_dim", "128"])
+    text = capsys.readouterr().out
+    assert "Validation F1 micro:" in text and "Validation F1 macro:" in text and "Average batch time:" in text
+    assert out["num_sample"] == (5, 5) and out["fused_engine"]
+    assert len(out["losses"]) == 3 * int(np.ceil(2167 / 128))
+    assert out["f1_micro"] > 0.8
+    assert out["losses"][-1] < out["losses"][0]
