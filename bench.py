@@ -249,14 +249,16 @@ def run_b200(args):
         lr = gdist.dp_lr(args.lr, world)   # mean over the global batch = sum of rank means / world
         eng.grad_scale = gdist.local_grad_scale(B, B * world, world)
         dp_mode = os.environ.get("GSAGE_DP", "peer")
-        if dp_mode == "peer":
+        if dp_mode == "none":            # diagnosis only: no gradient exchange (ranks diverge); never a bench line
+            pass
+        elif dp_mode == "peer":
             # all-reduce fused into the SGD kernel over NVLink peer memory: stays inside the step's CUDA graph
             try:
                 eng.peer = gdist.PeerAllreduceSGD(eng.flat_w.numel(), dev)
             except Exception as e:            # no symmetric-memory support on this box: NCCL between graphs
                 print("peer all-reduce unavailable (%s); falling back to NCCL" % str(e).splitlines()[0], file=sys.stderr)
                 dp_mode = "nccl"
-        ok = torch.tensor([1 if dp_mode == "peer" else 0], device=dev)
+        ok = torch.tensor([1 if dp_mode in ("peer", "none") else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             dp_mode, eng.peer = "nccl", None
@@ -264,7 +266,7 @@ def run_b200(args):
             allreduce = gdist.make_allreduce()
 
     args.dp_mode = {"peer": "fused into the SGD kernel over NVLink peer memory", "nccl": "NCCL between graphs",
-                    "none": "n/a"}[dp_mode]
+                    "none": "n/a" if world == 1 else "DISABLED (diagnostic run, not a result)"}[dp_mode]
     # ---- (1) device-resident throughput: inputs already in HBM, one graph replay per step.
     # Steps are software-pipelined three deep: while batch i is in its GEMM/backward chain, batch
     # i+1 is in its feature gather and batch i+2 in its sampler chain on side streams (all inside
@@ -315,16 +317,21 @@ def run_b200(args):
     nxt = lambda i: [(pool_nodes[(i + j) % pool], pool_labels[(i + j) % pool]) for j in (1, 2)]
 
     def e2e_step(i):
-        return model.train_step(pool_nodes[i % pool], pool_labels[i % pool], lr=lr, prefetch=nxt(i))
+        return model.train_step(pool_nodes[i % pool], pool_labels[i % pool], lr=lr, prefetch=nxt(i), sync=False)
 
     for i in range(3):
-        e2e_step(i)
+        float(e2e_step(i))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ev0.record()
-    for i in range(K):
-        e2e_loss = e2e_step(3 + i)
+    pending = None
+    for i in range(K):                      # every step's loss is read back; the read of step i is consumed
+        h = e2e_step(3 + i)                 # after step i+1 has been launched (one step of host run-ahead)
+        if pending is not None:
+            e2e_loss = float(pending)
+        pending = h
+    e2e_loss = float(pending)
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -388,7 +395,7 @@ def run_b200(args):
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(args, B),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 + 12 * B, "d2h_bytes_per_step": 4,
-                        "api": "SupervisedGraphSage.train_step(host ids, host labels, prefetch=[next two host batches]) -> float loss",
+                        "api": "SupervisedGraphSage.train_step(host ids, host labels, prefetch=[next two host batches], sync=False) -> loss handle, float() of it one step later",
                         "reference_loop_api": api_value},
                 "gpu_launches": eng.launches_per_step * K if hasattr(eng, "launches_per_step") else None,
                 "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu, "kernels_ms": kernels,

@@ -63,11 +63,15 @@ allreduce_sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t
     // 3. pull, add in rank order, update
     float4* p4 = reinterpret_cast<float4*>(p);
     for (int64_t i = lo + threadIdx.x; i < hi; i += kPeerThreads) {
+        // all peers' loads are issued before the first is consumed: one NVLink round trip, not `world`
+        float4 v[kMaxPeers];
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)
+            if (q < world) v[q] = ld_peer_v4(reinterpret_cast<const float4*>(stage[q]) + half + i);
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < world; ++q) {
-            const float4 v = ld_peer_v4(reinterpret_cast<const float4*>(stage[q]) + half + i);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)
+            if (q < world) { s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w; }
         float4 w = p4[i];
         w.x = w.x - lr * s.x; w.y = w.y - lr * s.y; w.z = w.z - lr * s.z; w.w = w.w - lr * s.w;
         p4[i] = w;
@@ -87,11 +91,11 @@ allreduce_sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t
 }  // namespace
 
 extern "C" int32_t gs_allreduce_sgd_blocks(int64_t n) {
-    // one CTA per ~2 K float4 (32 KB slice per peer), at most 64 CTAs: the kernel shares the GPU with the
-    // next batch's gather, and the CTAs spin while the slowest peer catches up
-    int64_t b = (n / 4 + 2047) / 2048;
+    // one float4 per thread per pass and at most one CTA per SM: the pull is NVLink-latency bound (a few
+    // hundred KB in total), so width, not depth; the CTAs spin only while the slowest peer catches up
+    int64_t b = (n / 4 + kPeerThreads - 1) / kPeerThreads;
     if (b < 1) b = 1;
-    if (b > 64) b = 64;
+    if (b > GS_NUM_SMS) b = GS_NUM_SMS;
     return (int32_t)b;
 }
 

@@ -122,6 +122,8 @@ class TrainEngine:
         self._warm = set()
         self._launch_count = {}
         self._side = self._gstream = self._sstream = None
+        self._loss_ring = None
+        self._pending_lr = None
         self.queue = []            # batches in flight: {slot, b, state (0 staged, 1 sampled, 2 gathered), ids}
         self.grad_scale = 1.0      # data parallel: n_local * world / n_global (dist.local_grad_scale)
 
@@ -239,6 +241,9 @@ class TrainEngine:
         self._gather_chain(fs, b)
         self._compute_chain(fs, b)
 
+    # streaming mode defers a step's SGD (or all-reduce + SGD) to the head of the next step's graph: measured
+    # 0.279 vs 0.297 ms/step on 1 GPU, 0.284 vs 0.371 on 2 (profiles/README.md); GSAGE_DEFER_UPDATE=0 disables
+    defer_update = bool(int(__import__('os').environ.get('GSAGE_DEFER_UPDATE', '1')))
     peer = None        # dist.PeerAllreduceSGD: data parallel with the all-reduce fused into the update kernel
 
     def _update(self, lr):
@@ -247,10 +252,12 @@ class TrainEngine:
         else:
             ops.sgd_step(self.flat_w, self.flat_g, lr)
 
-    def _overlapped(self, p, b0, b1, b2, lr):
+    def _overlapped(self, p, b0, b1, b2, lr, lead_lr=None):
         """One pipelined step as a fork/join over three streams (captured as ONE CUDA graph):
         compute chain of set p on the current stream || gather of set p+1 || sample chain of set
-        p+2.  b1 / b2 are None when the queue is shorter (tail of a run)."""
+        p+2.  b1 / b2 are None when the queue is shorter (tail of a run).  ``lead_lr``: apply the
+        PREVIOUS step's deferred update first (data parallel, see step_pipelined); ``lr=None``: leave
+        this step's update to the next call."""
         main = torch.cuda.current_stream()
         if b1 is not None:
             self._gstream.wait_stream(main)
@@ -260,6 +267,8 @@ class TrainEngine:
             self._sstream.wait_stream(main)
             with torch.cuda.stream(self._sstream):
                 self._sample_chain(self.sets[(p + 2) % self.depth], b2)
+        if lead_lr is not None:
+            self._update(lead_lr)
         self._compute_chain(self.sets[p], b0)
         if lr is not None:
             self._update(lr)
@@ -335,6 +344,7 @@ class TrainEngine:
         return b
 
     def forward_backward(self, b):
+        self.flush_update()
         self._run(("fb", b, self.cur), lambda: self._forward_backward(b))
 
     def update(self, lr):
@@ -343,6 +353,7 @@ class TrainEngine:
     def train_step(self, b, lr, allreduce=None):
         """fwd + bwd (+ gradient all-reduce) + SGD on the staged batch; returns nothing (the
         loss stays in ``self.loss`` on the device)."""
+        self.flush_update()
         if allreduce is None:
             self._run(("step", b, float(lr), self.cur), lambda: (self._forward_backward(b), self._update(lr)))
         else:
@@ -368,7 +379,15 @@ class TrainEngine:
             self._sstream = torch.cuda.Stream(device=self.dev, priority=-1)
         self._side = self._gstream
 
+    def flush_update(self):
+        """Apply a deferred weight update (data-parallel pipelining defers the all-reduce + SGD of a step
+        to the head of the next step's graph); call before reading the weights mid-run."""
+        if self._pending_lr is not None:
+            lr, self._pending_lr = self._pending_lr, None
+            self.update(lr)
+
     def reset_pipeline(self):
+        self.flush_update()
         self.queue = []
         self.cur = 0
 
@@ -406,7 +425,17 @@ class TrainEngine:
         b1 = q[1]["b"] if len(q) > 1 else None
         b2 = q[2]["b"] if len(q) > 2 else None
         if allreduce is None:
-            self._run(("pipe", p, b0, b1, b2, float(lr)), lambda: self._overlapped(p, b0, b1, b2, lr))
+            # The update of this step (SGD, or all-reduce + SGD with self.peer) is deferred to the head of
+            # the NEXT step's graph: it (and, data parallel, the wait for the slowest rank) then overlaps
+            # the next batch's gather instead of holding the fork/join of this graph open.  Every forward
+            # sees the same weights as without deferral; the last step of a run (nothing queued behind
+            # it) updates immediately, flush_update() does so on demand.
+            lead, self._pending_lr = self._pending_lr, None
+            defer = (self.peer is not None or self.defer_update) and b1 is not None
+            self._run(("pipe", p, b0, b1, b2, float(lr), lead, defer),
+                      lambda: self._overlapped(p, b0, b1, b2, None if defer else lr, lead))
+            if defer:
+                self._pending_lr = float(lr)
         else:
             # data parallel: the NCCL all-reduce is enqueued eagerly (capturing a collective inside a
             # forked graph deadlocked across ranks), so each stage is its own graph on its own stream:
@@ -439,6 +468,33 @@ class TrainEngine:
         self.loss_host.copy_(self.loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(self.loss_host[0])
+
+    def read_loss_async(self):
+        """Enqueue the device->host copy of this step's loss and return a handle; ``float(handle)`` waits
+        for that copy only, so the host can launch the next step before reading this one's result."""
+        if self._loss_ring is None:
+            self._loss_ring = [(torch.empty(1, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
+            self._loss_slot = 0
+        buf, ev = self._loss_ring[self._loss_slot]
+        self._loss_slot = (self._loss_slot + 1) % len(self._loss_ring)
+        buf.copy_(self.loss, non_blocking=True)
+        ev.record()
+        return PendingLoss(buf, ev)
+
+
+class PendingLoss:
+    """Loss of a step whose device->host copy is in flight (``train_step(..., sync=False)``)."""
+
+    def __init__(self, buf, event):
+        self._buf, self._event, self._value = buf, event, None
+
+    def __float__(self):
+        if self._value is None:
+            self._event.synchronize()
+            self._value = float(self._buf[0])
+        return self._value
+
+    item = __float__
 
 
 class _EngineLoss(torch.autograd.Function):

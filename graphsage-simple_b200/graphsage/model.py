@@ -83,15 +83,21 @@ class SupervisedGraphSage(nn.Module):
 
     grad_allreduce = None   # data parallel: callable(flat_grads) run between backward and the SGD step
 
-    def train_step(self, nodes, labels, lr=0.7, prefetch=None):
+    def train_step(self, nodes, labels, lr=0.7, prefetch=None, sync=True):
         """The reference's timed unit (model.py:246-250: zero_grad, loss, backward, SGD step) as
-        one fused call; returns the loss as a Python float (one 4-byte device->host read).
+        one fused call; returns the loss as a Python float (one 4-byte device->host read).  With
+        ``sync=False`` the read is enqueued and an ``engine.PendingLoss`` is returned: ``float()`` of it
+        waits for that step only, so the host can launch the next step before consuming this loss
+        (at most 8 may be outstanding).
 
         ``prefetch`` names the minibatches that FOLLOW this one -- ``(nodes, labels)`` or a list of
         up to two such pairs -- so that their neighbour sampling and feature gather run on side
         streams while this batch is in its GEMM/backward chain (the data-loader style overlap the
         reference's single Python thread cannot do).  Pass the same batches, in order, as
-        ``nodes, labels`` of the following calls; results equal plain sequential steps."""
+        ``nodes, labels`` of the following calls; results equal plain sequential steps.  While batches
+        are announced the engine is in streaming mode: the SGD update of a step is enqueued at the head
+        of the next step, so read the weights after the last batch (no ``prefetch``) or after
+        ``model._engine.flush_update()``."""
         from .engine import engine_for
         from . import sampling
         upcoming = [] if prefetch is None else ([prefetch] if isinstance(prefetch, tuple) else list(prefetch))
@@ -102,7 +108,7 @@ class SupervisedGraphSage(nn.Module):
             if not upcoming and not eng.queue:
                 b = eng.stage(nodes, labels, step)
                 eng.train_step(b, lr, self.grad_allreduce)
-                return eng.read_loss()
+                return eng.read_loss() if sync else eng.read_loss_async()
             same = lambda entry, ids: entry["ids"] is not None and len(entry["ids"]) == len(ids) and \
                 np.array_equal(entry["ids"], np.asarray(ids, dtype=np.int64))
             if not eng.queue or not same(eng.queue[0], nodes):
@@ -115,7 +121,7 @@ class SupervisedGraphSage(nn.Module):
                     eng.push(nn, ll, step + 1 + j)
             del eng.queue[len(upcoming) + 1:]
             eng.step_pipelined(lr, self.grad_allreduce)
-        return eng.read_loss()
+        return eng.read_loss() if sync else eng.read_loss_async()
 
 
 # ------------------------------------------------------------------------------------------------
