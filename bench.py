@@ -276,11 +276,16 @@ def run_b200(args):
     d_labels = torch.from_numpy(pool_labels).to(dev)
     model.grad_allreduce = allreduce
     eng.reset_pipeline()
-    eng.push(d_nodes[0], d_labels[0], 1, on_device=True)
-    eng.push(d_nodes[1], d_labels[1], 2, on_device=True)
+    # device-resident inputs: one pre-packed staging block [sampler step | labels | targets] per batch of the
+    # pool, already in HBM; a step's staging is ONE device-to-device copy of 12 KB
+    total = W + 5 + K + 2
+    d_blocks = torch.stack([eng.pack_stage(pool_nodes[i % pool], pool_labels[i % pool], i + 1)
+                            for i in range(total)]).to(dev)
+    eng.push(None, None, None, packed=(d_blocks[0], B))
+    eng.push(None, None, None, packed=(d_blocks[1], B))
 
     def device_step(i):
-        eng.push(d_nodes[(i + 2) % pool], d_labels[(i + 2) % pool], i + 3, on_device=True)
+        eng.push(None, None, None, packed=(d_blocks[i + 2], B))
         eng.step_pipelined(lr, allreduce)
 
     for i in range(W + 5):                 # includes the eager + capture iterations of both parities
@@ -432,7 +437,7 @@ def profile_kernels(eng, B, lr, d_nodes, d_labels, iters=5):
         setattr(ops, name, timed)
 
     for nm in ("sample_csr", "dedup_remap", "gather_mean_fwd", "encoder_fwd", "encoder_fwd_tc", "classifier_xent",
-               "encoder_bwd", "encoder_wgrad_tc", "encoder_dgrad", "scatter_mean_bwd", "head_fwd_bwd", "sgd_step"):
+               "encoder_bwd", "encoder_wgrad_tc", "encoder_dgrad", "scatter_mean_bwd", "head_rows", "head_wgrad", "sgd_step"):
         wrap(nm)
     try:
         for it in range(iters + 1):

@@ -408,37 +408,53 @@ extern "C" int64_t gs_head_ws_floats(int32_t n, int32_t k2_in, int32_t num_class
     return ((nn * kD2 + nn * num_classes + nn + 3) & ~(int64_t)3) + (int64_t)tiles * kSplits * (kTM * kTN) + tiles;
 }
 
-extern "C" int gs_head_fwd_bwd(const float* h1, int64_t ld_h1, int32_t d1,
-                               const int32_t* idx, const int32_t* cnt, int32_t width, const int32_t* self_slots,
-                               const float* w2, int64_t ld_w2, int32_t d2, int32_t act2,
-                               const float* wc, int64_t ld_wc, int32_t num_classes,
-                               const int64_t* labels, int32_t n, float grad_scale,
-                               float* comb2, int64_t ld_comb2, float* h2, int64_t ld_h2,
-                               float* logits, int64_t ld_logits, float* loss,
-                               float* gh1, int64_t ld_gh1, float* gw2, int64_t ld_gw2, float* gwc, int64_t ld_gwc,
-                               float* ws, void* stream) {
-    if (!h1 || !idx || !cnt || !w2 || !wc || !labels || !comb2 || !h2 || !gh1 || !gw2 || !gwc || !ws || n <= 0 || width <= 0)
+namespace {
+
+struct HeadPlan {
+    int K2, tiles, tiles_w2, tn_w2;
+    float *dz2, *dl, *loss_rows, *part;
+    int32_t* tickets;
+};
+
+int head_plan(int32_t d1, int32_t d2, int32_t num_classes, int32_t n, bool sage, float* ws, HeadPlan* hp) {
+    hp->K2 = sage ? 2 * d1 : d1;
+    if (!gs_head_supported(d1, hp->K2, d2, num_classes)) return GS_ENOSUP;
+    hp->tiles = wgrad_tiles(hp->K2, num_classes, &hp->tiles_w2, &hp->tn_w2);
+    hp->dz2 = ws;
+    hp->dl = hp->dz2 + (int64_t)n * kD2;
+    hp->loss_rows = hp->dl + (int64_t)n * num_classes;
+    hp->part = ws + (((int64_t)n * kD2 + (int64_t)n * num_classes + n + 3) & ~(int64_t)3);
+    hp->tickets = reinterpret_cast<int32_t*>(hp->part + (int64_t)hp->tiles * kSplits * (kTM * kTN));
+    return GS_OK;
+}
+
+}  // namespace
+
+extern "C" int gs_head_rows(const float* h1, int64_t ld_h1, int32_t d1,
+                            const int32_t* idx, const int32_t* cnt, int32_t width, const int32_t* self_slots,
+                            const float* w2, int64_t ld_w2, int32_t d2, int32_t act2,
+                            const float* wc, int64_t ld_wc, int32_t num_classes,
+                            const int64_t* labels, int32_t n, float grad_scale,
+                            float* comb2, int64_t ld_comb2, float* h2, int64_t ld_h2,
+                            float* logits, int64_t ld_logits, float* gh1, int64_t ld_gh1,
+                            float* ws, void* stream) {
+    if (!h1 || !idx || !cnt || !w2 || !wc || !labels || !comb2 || !h2 || !gh1 || !ws || n <= 0 || width <= 0)
         return GS_EINVAL;
-    const int K2 = self_slots ? 2 * d1 : d1;
-    if (!gs_head_supported(d1, K2, d2, num_classes)) return GS_ENOSUP;
+    HeadPlan hp;
+    int rc = head_plan(d1, d2, num_classes, n, self_slots != nullptr, ws, &hp);
+    if (rc) return rc;
     if (!gs_aligned16(h1) || !gs_aligned16(w2) || !gs_aligned16(wc) || !gs_aligned16(comb2) || !gs_aligned16(gh1) ||
-        !gs_aligned16(ws) || !gs_aligned16(h2) || (ld_h1 & 3) || (ld_w2 & 3) || (ld_wc & 3) || (ld_comb2 & 3) || (ld_gh1 & 3) || (ld_h2 & 3))
+        !gs_aligned16(ws) || !gs_aligned16(h2) || (ld_h1 & 3) || (ld_w2 & 3) || (ld_wc & 3) || (ld_comb2 & 3) ||
+        (ld_gh1 & 3) || (ld_h2 & 3))
         return GS_EALIGN;
     cudaStream_t s = (cudaStream_t)stream;
-    int tiles_w2, tn_w2;
-    const int tiles = wgrad_tiles(K2, num_classes, &tiles_w2, &tn_w2);
-    float* dz2 = ws;
-    float* dl = dz2 + (int64_t)n * kD2;
-    float* loss_rows = dl + (int64_t)n * num_classes;
-    float* part = ws + (((int64_t)n * kD2 + (int64_t)n * num_classes + n + 3) & ~(int64_t)3);
-    int32_t* tickets = reinterpret_cast<int32_t*>(part + (int64_t)tiles * kSplits * (kTM * kTN));
-
     HeadArgs a{h1, ld_h1, d1, idx, cnt, width, self_slots, w2, ld_w2, act2, wc, ld_wc, num_classes, labels, n,
-               grad_scale / (float)n, comb2, ld_comb2, h2, ld_h2, logits, ld_logits, gh1, ld_gh1, dz2, dl, loss_rows};
-    const size_t smem = head_smem_bytes(K2, num_classes);
+               grad_scale / (float)n, comb2, ld_comb2, h2, ld_h2, logits, ld_logits, gh1, ld_gh1, hp.dz2, hp.dl,
+               hp.loss_rows};
+    const size_t smem = head_smem_bytes(hp.K2, num_classes);
     static size_t attr256 = 0, attr128 = 0;
     const int blocks = (n + kRows - 1) / kRows;
-    if (K2 == 256) {
+    if (hp.K2 == 256) {
         if (smem > attr256) {
             cudaError_t e = cudaFuncSetAttribute(head_rows_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
@@ -454,10 +470,38 @@ extern "C" int gs_head_fwd_bwd(const float* h1, int64_t ld_h1, int32_t d1,
         head_rows_kernel<128><<<blocks, kThreads, smem, s>>>(a);
     }
     GS_LAUNCH_CHECK();
-    WgradArgs b{dz2, comb2, ld_comb2, K2, dl, num_classes, h2, ld_h2, n, gw2, ld_gw2, gwc, ld_gwc, part, tickets,
-                loss_rows, loss, tiles_w2, tn_w2};
+    return GS_OK;
+}
+
+extern "C" int gs_head_wgrad(const float* comb2, int64_t ld_comb2, const float* h2, int64_t ld_h2,
+                             int32_t d1, int32_t d2, int32_t num_classes, int32_t n, int32_t sage,
+                             float* loss, float* gw2, int64_t ld_gw2, float* gwc, int64_t ld_gwc,
+                             float* ws, void* stream) {
+    if (!comb2 || !h2 || !gw2 || !gwc || !ws || n <= 0) return GS_EINVAL;
+    HeadPlan hp;
+    int rc = head_plan(d1, d2, num_classes, n, sage != 0, ws, &hp);
+    if (rc) return rc;
+    if (!gs_aligned16(comb2) || !gs_aligned16(h2) || !gs_aligned16(ws) || (ld_comb2 & 3) || (ld_h2 & 3)) return GS_EALIGN;
+    WgradArgs b{hp.dz2, comb2, ld_comb2, hp.K2, hp.dl, num_classes, h2, ld_h2, n, gw2, ld_gw2, gwc, ld_gwc, hp.part,
+                hp.tickets, hp.loss_rows, loss, hp.tiles_w2, hp.tn_w2};
     GS_PREFER_SMEM(head_wgrad_kernel);
-    head_wgrad_kernel<<<dim3(tiles, kSplits), 256, 0, s>>>(b);
+    head_wgrad_kernel<<<dim3(hp.tiles, kSplits), 256, 0, (cudaStream_t)stream>>>(b);
     GS_LAUNCH_CHECK();
     return GS_OK;
+}
+
+extern "C" int gs_head_fwd_bwd(const float* h1, int64_t ld_h1, int32_t d1,
+                               const int32_t* idx, const int32_t* cnt, int32_t width, const int32_t* self_slots,
+                               const float* w2, int64_t ld_w2, int32_t d2, int32_t act2,
+                               const float* wc, int64_t ld_wc, int32_t num_classes,
+                               const int64_t* labels, int32_t n, float grad_scale,
+                               float* comb2, int64_t ld_comb2, float* h2, int64_t ld_h2,
+                               float* logits, int64_t ld_logits, float* loss,
+                               float* gh1, int64_t ld_gh1, float* gw2, int64_t ld_gw2, float* gwc, int64_t ld_gwc,
+                               float* ws, void* stream) {
+    int rc = gs_head_rows(h1, ld_h1, d1, idx, cnt, width, self_slots, w2, ld_w2, d2, act2, wc, ld_wc, num_classes,
+                          labels, n, grad_scale, comb2, ld_comb2, h2, ld_h2, logits, ld_logits, gh1, ld_gh1, ws, stream);
+    if (rc) return rc;
+    return gs_head_wgrad(comb2, ld_comb2, h2, ld_h2, d1, d2, num_classes, n, self_slots != nullptr, loss, gw2, ld_gw2,
+                         gwc, ld_gwc, ws, stream);
 }

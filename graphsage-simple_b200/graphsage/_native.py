@@ -44,6 +44,10 @@ SIGNATURES = {
     "gs_head_fwd_bwd": (_i32, [_ptr, _i64, _i32, _ptr, _ptr, _i32, _ptr, _ptr, _i64, _i32, _i32, _ptr, _i64, _i32,
                                _ptr, _i32, _f32, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64,
                                _ptr, _i64, _ptr, _ptr]),
+    "gs_head_rows": (_i32, [_ptr, _i64, _i32, _ptr, _ptr, _i32, _ptr, _ptr, _i64, _i32, _i32, _ptr, _i64, _i32,
+                            _ptr, _i32, _f32, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _ptr]),
+    "gs_head_wgrad": (_i32, [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr, _i64, _ptr, _i64,
+                             _ptr, _ptr]),
     "gs_sgd_step": (_i32, [_ptr, _ptr, _f32, _i64, _ptr]),
     "gs_allreduce_sgd_blocks": (_i32, [_i64]),
     "gs_allreduce_sgd": (_i32, [_ptr, _ptr, _i64, _f32, _ptr, _ptr, _i32, _i32, _ptr, _ptr]),

@@ -204,10 +204,14 @@ class TrainEngine:
         comb2, h2 = self.comb2[:b], self.h2[:b]
         if self.head:
             main.wait_stream(self._aux)
-            ops.head_fwd_bwd(self.h1, self.d1, idx2, cnt2, None if self.gcn else self.self2[:b], self.w2, self.act2,
-                             self.wc, labels, self.grad_scale, comb2, h2, self.logits[:b], self.loss, self.gh1,
-                             self.gw2, self.gwc, self.head_ws)
+            ops.head_rows(self.h1, self.d1, idx2, cnt2, None if self.gcn else self.self2[:b], self.w2, self.act2,
+                          self.wc, labels, self.grad_scale, comb2, h2, self.logits[:b], self.gh1, self.head_ws)
+            # the head's weight gradients only feed the update: forked, concurrent with the layer-1 backward
+            self._aux.wait_stream(main)
+            with torch.cuda.stream(self._aux):
+                ops.head_wgrad(comb2, h2, self.d1, self.C, not self.gcn, self.loss, self.gw2, self.gwc, self.head_ws)
             self._wgrad1(fs, comb1, h1, gh1)
+            main.wait_stream(self._aux)
             return
         ops.gather_mean_fwd(self.h1, self.d1, idx2, cnt2, comb2, neigh_off=0 if self.gcn else self.d1,
                             self_ids=None if self.gcn else self.self2[:b])
@@ -343,6 +347,21 @@ class TrainEngine:
         fs.step_dev.fill_(int(step))
         return b
 
+    def pack_stage(self, nodes, labels, step):
+        """Host-side: one staging block [step | labels | targets] (uint8 tensor) for ``stage_packed``."""
+        blk = torch.zeros(8 + 12 * self.B, dtype=torch.uint8)
+        b = len(nodes)
+        blk[:8].view(torch.int64)[0] = int(step)
+        blk[8:8 + 8 * b].view(torch.int64).copy_(torch.as_tensor(np.asarray(labels, dtype=np.int64).reshape(-1)))
+        blk[8 + 8 * self.B:8 + 8 * self.B + 4 * b].view(torch.int32).copy_(torch.as_tensor(np.asarray(nodes, dtype=np.int32)))
+        return blk
+
+    def stage_packed(self, block, b, slot=None):
+        """Stage a pre-packed block (``pack_stage``; device- or pinned-host-resident) with ONE copy."""
+        fs = self.sets[self.cur if slot is None else slot]
+        fs.stage_dev.copy_(block, non_blocking=True)
+        return b
+
     def forward_backward(self, b):
         self.flush_update()
         self._run(("fb", b, self.cur), lambda: self._forward_backward(b))
@@ -391,16 +410,20 @@ class TrainEngine:
         self.queue = []
         self.cur = 0
 
-    def push(self, nodes, labels, step, on_device=False):
-        """Stage the next minibatch (host ids/labels, or device tensors with ``on_device``) into the
-        next free frontier set and append it to the pipeline queue."""
+    def push(self, nodes, labels, step, on_device=False, packed=None):
+        """Stage the next minibatch (host ids/labels, device tensors with ``on_device``, or a block made
+        by ``pack_stage`` with ``packed=(block, b)``) into the next free frontier set and append it to the
+        pipeline queue."""
         self.enable_pipeline()
         if len(self.queue) >= self.depth:
             raise RuntimeError("pipeline queue is full (%d batches in flight)" % self.depth)
         slot = (self.cur + len(self.queue)) % self.depth
-        b = (self.stage_device if on_device else self.stage)(nodes, labels, step, slot=slot)
+        if packed is not None:
+            b = self.stage_packed(packed[0], packed[1], slot=slot)
+        else:
+            b = (self.stage_device if on_device else self.stage)(nodes, labels, step, slot=slot)
         self.queue.append({"slot": slot, "b": b, "state": 0,
-                           "ids": None if on_device else np.array(nodes, dtype=np.int64, copy=True)})
+                           "ids": None if (on_device or packed is not None) else np.array(nodes, dtype=np.int64, copy=True)})
         return b
 
     def step_pipelined(self, lr, allreduce=None):

@@ -263,6 +263,29 @@ def head_fwd_bwd(h1, d1, idx, cnt, self_slots, w2, act2, wc, labels, grad_scale,
     return loss
 
 
+def head_rows(h1, d1, idx, cnt, self_slots, w2, act2, wc, labels, grad_scale, comb2, h2, logits, gh1, ws):
+    """First launch of the fused head (everything row-local) -- see gs_head_rows."""
+    lib = N.load()
+    N.require_cuda(h1, idx, cnt, w2, wc, labels, comb2, h2, gh1, ws)
+    n, width = idx.shape
+    N.check(lib.gs_head_rows(N.ptr(h1), h1.stride(0), int(d1), N.ptr(idx), N.ptr(cnt), width, N.ptr(self_slots),
+                             N.ptr(w2), w2.stride(0), w2.shape[0], int(act2), N.ptr(wc), wc.stride(0), wc.shape[0],
+                             N.ptr(labels), n, float(grad_scale), N.ptr(comb2), comb2.stride(0),
+                             N.ptr(h2), h2.stride(0), N.ptr(logits), logits.stride(0) if logits is not None else 0,
+                             N.ptr(gh1), gh1.stride(0), N.ptr(ws), N.stream()), "gs_head_rows")
+    LAUNCHES[0] += 1
+
+
+def head_wgrad(comb2, h2, d1, num_classes, sage, loss, gw2, gwc, ws):
+    """Second launch of the fused head (weight gradients + mean loss) -- see gs_head_wgrad."""
+    lib = N.load()
+    N.require_cuda(comb2, h2, gw2, gwc, ws)
+    N.check(lib.gs_head_wgrad(N.ptr(comb2), comb2.stride(0), N.ptr(h2), h2.stride(0), int(d1), h2.shape[1],
+                              int(num_classes), comb2.shape[0], int(bool(sage)), N.ptr(loss), N.ptr(gw2), gw2.stride(0),
+                              N.ptr(gwc), gwc.stride(0), N.ptr(ws), N.stream()), "gs_head_wgrad")
+    LAUNCHES[0] += 1
+
+
 def sgd_step(p, g, lr):
     lib = N.load()
     N.require_cuda(p, g)

@@ -184,6 +184,22 @@ GS_API int gs_head_fwd_bwd(const float* h1, int64_t ld_h1, int32_t d1,
                     float* gh1, int64_t ld_gh1, float* gw2, int64_t ld_gw2, float* gwc, int64_t ld_gwc,
                     float* ws, void* stream);
 
+/* The two launches of gs_head_fwd_bwd separately, so that a caller can run the weight gradients
+ * (gs_head_wgrad: gw2, gwc, loss; reads what gs_head_rows left in comb2, h2 and ws) on another
+ * stream, concurrently with the inner layer's backward, which only needs gh1.               */
+GS_API int gs_head_rows(const float* h1, int64_t ld_h1, int32_t d1,
+                 const int32_t* idx, const int32_t* cnt, int32_t width, const int32_t* self_slots,
+                 const float* w2, int64_t ld_w2, int32_t d2, int32_t act2,
+                 const float* wc, int64_t ld_wc, int32_t num_classes,
+                 const int64_t* labels, int32_t n, float grad_scale,
+                 float* comb2, int64_t ld_comb2, float* h2, int64_t ld_h2,
+                 float* logits, int64_t ld_logits, float* gh1, int64_t ld_gh1,
+                 float* ws, void* stream);
+GS_API int gs_head_wgrad(const float* comb2, int64_t ld_comb2, const float* h2, int64_t ld_h2,
+                  int32_t d1, int32_t d2, int32_t num_classes, int32_t n, int32_t sage,
+                  float* loss, float* gw2, int64_t ld_gw2, float* gwc, int64_t ld_gwc,
+                  float* ws, void* stream);
+
 /* ---- K6: SGD -----------------------------------------------------------------------------
  * Replaces torch.optim.SGD(lr=0.7).step(), graphsage/model.py:237, 250: p -= lr * g.      */
 GS_API int gs_sgd_step(float* p, const float* g, float lr, int64_t n, void* stream);
