@@ -58,3 +58,19 @@ def test_cli_with_intended_knobs(setup, capsys):
     assert len(out["losses"]) == 3 * int(np.ceil(2167 / 128))
     assert out["f1_micro"] > 0.8
     assert out["losses"][-1] < out["losses"][0]
+
+
+def test_pubmed_shape_config_trains_on_the_fused_engine(tmp_path):
+    """BASELINE config 2: Pubmed-shape (19 717 nodes, 500-d), 2-layer mean, fan-out 10/25, hidden 128/128 --
+    the shape that takes the tcgen05 layer-1 GEMMs and the fused head.  (No reference golden: the reference's
+    as-run driver needs a 15 774 x ~19 000 dense mask per step.)"""
+    from graphsage import data as D
+    from graphsage.model import run_model
+    root = str(tmp_path)
+    D.write_synthetic_dataset("pubmed", root, seed=31)
+    out = run_model("pubmed", "None", 1, 1, data_root=root, identity_dim=128, batch_size=1024, gcn=False, verbose=False)
+    eng = out["model"]._engine
+    assert out["fused_engine"] and eng.tc1 and eng.head and out["num_sample"] == (10, 25)
+    assert len(out["losses"]) == int(np.ceil(15774 / 1024)) and np.isfinite(out["losses"]).all()
+    assert out["losses"][-1] < out["losses"][0]
+    assert out["f1_micro"] > 0.6                      # 3 planted classes, chance = 0.33
