@@ -384,9 +384,17 @@ def run_b200(args):
         g1_bytes = (s1 + n1) * args.feat * 4 + (s1 + 2 * n1) * 4 + n1 * 2 * args.feat * 4
         g1_ms = kernels["gather_mean_fwd[layer1]"]
         ach = g1_bytes / (g1_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and (args.nodes, args.feat, args.batch, args.k1, args.k2) == (233000, 602, 1024, 10, 25):
+            tj = _j.load(open(tpath))           # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+            traffic_src = tj["source"]
         roofline = {"kernel": "gather_mean_kernel (layer 1: self row + mean of k1 neighbour rows -> comb1)",
                     "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "peak_source": which, "traffic": None,
+                    "peak_source": which, "traffic": traffic, "traffic_source": traffic_src,
+                    "timing": "kernel launched alone (eager, CUDA events on its stream, 5 launches), same launch "
+                              "configuration as inside the pipelined step",
                     "algorithmic_bytes_per_launch": g1_bytes,
                     "rows_read": s1 + n1, "n1": n1, "s1": s1, "s2": s2, "avg_launch_ms": g1_ms,
                     "step_share": g1_ms / sum(kernels.values())}
