@@ -53,17 +53,38 @@ def parse():
     ap.add_argument("--workload", default="reddit", choices=["reddit", "products"],
                     help="reddit: BASELINE config 4 (default, the judged line); products: config 5 -- 3-layer model, "
                          "feature table + CSR partitioned over the ranks, NCCL all-to-all per lookup")
+    ap.add_argument("--graph", default="uniform", choices=["uniform", "rmat"],
+                    help="uniform: default_rng(1) pairs (SURVEY s8d, the judged line); rmat: heavy-tailed variant "
+                         "(a,b,c = 0.57,0.19,0.19, same node count and pair count, every node >= 1 edge) for hub stress")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------ workload
-def build_graph_arrays(n, pairs):
+def rmat_pairs(n, pairs, rng, a=0.57, b=0.19, c=0.19):
+    """R-MAT edge generator (Chakrabarti et al.): one quadrant choice per bit, ids folded into [0, n)."""
+    bits = int(np.ceil(np.log2(n)))
+    src = np.zeros(pairs, dtype=np.int64)
+    dst = np.zeros(pairs, dtype=np.int64)
+    for _ in range(bits):
+        r = rng.random(pairs)
+        src = (src << 1) | (r >= a + b)
+        dst = (dst << 1) | (((r >= a) & (r < a + b)) | (r >= a + b + c))
+    perm = rng.permutation(1 << bits)                   # scatter the hubs over the id space
+    return np.stack([perm[src] % n, perm[dst] % n])
+
+
+def build_graph_arrays(n, pairs, kind="uniform"):
     """Reddit-shape synthetic graph of SURVEY.md s8d: default_rng(1) pairs, symmetrised,
-    deduplicated, rows sorted; every node has degree >= 1 with these sizes."""
+    deduplicated, rows sorted; every node has degree >= 1 with these sizes (rmat: a ring is added)."""
     rng = np.random.default_rng(1)
-    e = rng.integers(0, n, (2, pairs), dtype=np.int64)
+    if kind == "rmat":
+        e = rmat_pairs(n, pairs, rng)
+        ring = np.arange(n, dtype=np.int64)
+        e = np.concatenate([e, np.stack([ring, (ring + 1) % n])], axis=1)
+    else:
+        e = rng.integers(0, n, (2, pairs), dtype=np.int64)
     src = np.concatenate([e[0], e[1]])
     dst = np.concatenate([e[1], e[0]])
     key = np.unique(src * np.int64(n) + dst)
@@ -162,7 +183,7 @@ def run_reference(args):
         return
     args.dp_mode = "n/a"
     import torch
-    rowptr, col = build_graph_arrays(args.nodes, args.pairs)
+    rowptr, col = build_graph_arrays(args.nodes, args.pairs, args.graph)
     torch.manual_seed(1)
     table = torch.randn(args.nodes, args.feat)
     labels = np.random.default_rng(1).integers(0, args.classes, (args.nodes, 1)).astype(np.int64)
@@ -185,7 +206,8 @@ def run_reference(args):
 
 
 def workload_config(args, batch):
-    return {"workload": "synthetic Reddit-shape graph: %d nodes, %d undirected pairs (CSR ~2x), %d-d fp32 "
+    return {"workload": ("" if getattr(args, "graph", "uniform") == "uniform" else "[R-MAT heavy-tailed variant] ") +
+                        "synthetic Reddit-shape graph: %d nodes, %d undirected pairs (CSR ~2x), %d-d fp32 "
                         "features, %d classes, 2-layer SAGE-mean concat, hidden %d/%d, fan-out %d (targets) / "
                         "%d (hop-1), SGD" % (args.nodes, args.pairs, args.feat, args.classes, args.hidden,
                                             args.hidden, args.k2, args.k1),
@@ -215,7 +237,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    rowptr, col = build_graph_arrays(args.nodes, args.pairs)
+    rowptr, col = build_graph_arrays(args.nodes, args.pairs, args.graph)
     graph = CSRGraph(rowptr, col, dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1)
@@ -386,7 +408,7 @@ def run_b200(args):
         ach = g1_bytes / (g1_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath) and (args.nodes, args.feat, args.batch, args.k1, args.k2) == (233000, 602, 1024, 10, 25):
+        if os.path.exists(tpath) and (args.nodes, args.feat, args.batch, args.k1, args.k2, args.graph) == (233000, 602, 1024, 10, 25, "uniform"):
             tj = _j.load(open(tpath))           # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
             traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
             traffic_src = tj["source"]

@@ -31,6 +31,9 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+EXTRA = os.environ.get("GSAGE_NVCC_EXTRA", "").split()      # e.g. -DGS_TC_STAGES=3 (experiments)
+
+
 def build_native(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
@@ -43,7 +46,7 @@ def build_native(force=False, verbose=False):
         o = os.path.join(OBJ, src[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            jobs.append([NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([NVCC] + FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -199,10 +199,11 @@ extern "C" int gs_gather_mean_fwd(const float* table, int64_t ld_table, int32_t 
     // = 61 KB in flight per SM (Little: 6.5 TB/s x ~800 ns / 148 SMs = 35 KB).  Tunable for experiments.
     static int bps = 0, wpb = 0, carve = 0;
     if (bps == 0) {
-        // max-shared carveout: measured 0.292 ms/step vs 0.349 with the default split (the SM's split can only
-        // change when it is idle, so an L1-heavy resident gather keeps the 198 KB GEMM CTAs out); costs the
-        // gather ~10 % stand-alone (fewer outstanding L1 requests).  profiles/README.md, r01 sweep.
-        carve = getenv("GSAGE_GATHER_CARVEOUT") ? atoi(getenv("GSAGE_GATHER_CARVEOUT")) : 1;
+        // L1/shared split preference (percent of shared; 1 = max shared, 0 = driver default).  The split can only
+        // change on an idle SM, so a resident gather with the default (L1-heavy) split keeps the 145 KB GEMM CTAs
+        // and the 175 KB head CTAs out; max-shared starves the gather's outstanding loads of L1.  72 % = 164 KB
+        // shared / 92 KB L1 serves both (0.255 ms/step vs 0.275 max-shared, 0.30+ default; profiles/README.md s4).
+        carve = getenv("GSAGE_GATHER_CARVEOUT") ? atoi(getenv("GSAGE_GATHER_CARVEOUT")) : 72;
         const char* e = getenv("GSAGE_GATHER_BPS");
         bps = e ? atoi(e) : 3;
         if (bps < 1) bps = 1;
@@ -214,7 +215,10 @@ extern "C" int gs_gather_mean_fwd(const float* table, int64_t ld_table, int32_t 
     if (nblocks > GS_NUM_SMS * bps) nblocks = GS_NUM_SMS * bps;
     const dim3 grid(nblocks), block(wpb * 32);
     cudaStream_t s = (cudaStream_t)stream;
-#define GS_GM(CH, NB) if (carve) GS_PREFER_SMEM((gather_mean_kernel<CH, NB>)); gather_mean_kernel<CH, NB><<<grid, block, 0, s>>>(table, ld_table, dim, idx, cnt, width, \
+#define GS_GM(CH, NB) if (carve == 1) GS_PREFER_SMEM((gather_mean_kernel<CH, NB>)); \
+        else if (carve > 1) { static bool d__ = false; if (!d__) { cudaFuncSetAttribute((gather_mean_kernel<CH, NB>), \
+            cudaFuncAttributePreferredSharedMemoryCarveout, carve); d__ = true; } } \
+        gather_mean_kernel<CH, NB><<<grid, block, 0, s>>>(table, ld_table, dim, idx, cnt, width, \
         self_ids, n_max, n_dev, out, ld_out, neigh_off, align)
     if (nchunks <= 32) { GS_GM(1, 8); }
     else if (nchunks <= 64) { GS_GM(2, 4); }

@@ -16,7 +16,7 @@
 // the shared-memory read traffic of the MMAs, which (not the tensor pipe) bounded the first
 // version of this kernel (profiles/README.md, r01 tc_gemm v1 vs v2).
 //
-// Per CTA (192 threads, 1 CTA/SM): 4-stage smem ring of 48 KB (X raw, Y_hi, Y_lo), TMEM =
+// Per CTA (320 threads, 1 CTA/SM): 3-stage smem ring of 48 KB (X raw, Y_hi, Y_lo), TMEM =
 // 2 main accumulators + 1 correction accumulator (3 x 128 columns) + 2 A slots (2 x 64 columns).
 //   warp 0      TMA producer
 //   warps 2..5  splitter (smem -> registers -> TMEM A slot), later the epilogue
@@ -27,7 +27,13 @@
 
 namespace {
 
-constexpr int kStages = 4;
+// 3 stages (145 KB) instead of 4 (193 KB): alone the GEMMs lose ~9 % (fwd 73 -> 80 us, wgrad 69 -> 75 us), but the
+// SM can then run with a 164 KB shared / 92 KB L1 split, which the co-resident gather needs for its
+// outstanding loads: whole step 0.265 -> 0.255 ms (profiles/README.md s4).  -DGS_TC_STAGES=4 restores 4.
+#ifndef GS_TC_STAGES
+#define GS_TC_STAGES 3
+#endif
+constexpr int kStages = GS_TC_STAGES;
 constexpr int kTile = 128;            // M and N of the UMMA tile (d_out == 128)
 constexpr int kChunk = 32;            // reduction elements per stage: 32 fp32 = one 128-B swizzle row
 constexpr int kOperandBytes = kTile * kChunk * 4;          // 16 KB
@@ -319,9 +325,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int row = q * 32 + lane;                         // A/accumulator row handled by this thread
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t slot = tmem_a + lane_base + grp * kASlotCols;
-        for (int c = grp; c < nchunks; c += kASlots) {
+        for (int c = 0; c < nchunks; ++c) {
             const int s = c % kStages, it = c / kStages;
+            // EVERY chunk's full barrier is observed, also the other group's: a parity wait only tells phase k
+            // from phase k+1, and with an odd stage count the two groups alternate on a stage, so a group that
+            // skipped a phase could see "phase k-1 done" as "phase k+1 done" and split a tile that has not
+            // landed (measured: 3 stages, 50 % of the 26 000-row weight-gradient runs returned garbage).
             mbar_wait(bars + 8 * (kBarFull + s), it & 1);
+            if (c % kASlots != grp) continue;
             if (q == 2) TC_TRACE(4, c);
             const uint8_t* xs = gen_base + s * kStageBytes;
 #pragma unroll

@@ -377,3 +377,28 @@ def test_bucket_by_owner_bit_exact(ops, n, world, local):
     assert np.array_equal(send.cpu().numpy(), want)
     inv = np.empty(n, dtype=np.int64); inv[order] = np.arange(n)
     assert np.array_equal(perm.cpu().numpy(), inv)
+
+
+def test_encoder_tensor_core_repeatable(ops):
+    """Race regression: the 26 000-row shape (two waves of CTAs, 29-stage split-K partials) run 25 times must
+    give the same bits every time and stay inside the 1e-5 bar.  (A parity-aliasing race between the two
+    splitter groups once made half of these runs return garbage with a 3-stage ring, profiles/README.md s10.)"""
+    n, k_in, d_out, act = 26000, 1204, 128, 1
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = ops.empty_rows(n, k_in, "cuda")
+    x.copy_(torch.randn(n, k_in, device="cuda", generator=g))
+    w = torch.randn(d_out, k_in, device="cuda", generator=g) / k_in ** 0.5
+    gh = torch.randn(n, d_out, device="cuda", generator=g)
+    h0 = torch.empty((n, d_out), device="cuda")
+    ops.encoder_fwd_tc(x, w, act, h0)
+    gw0 = torch.empty((d_out, k_in), device="cuda")
+    ops.encoder_wgrad_tc(x, h0, gh, act, gw0)
+    hd = h0.double()
+    assert relerr(h0.cpu().numpy(), torch.relu(x.double() @ w.double().t()).cpu().numpy()) < REL
+    assert relerr(gw0.cpu().numpy(), ((gh.double() * (hd > 0).double()).t() @ x.double()).cpu().numpy()) < REL
+    for _ in range(25):
+        h = torch.full((n, d_out), float("nan"), device="cuda")
+        ops.encoder_fwd_tc(x, w, act, h)
+        gw = torch.full((d_out, k_in), float("nan"), device="cuda")
+        ops.encoder_wgrad_tc(x, h0, gh, act, gw)
+        assert torch.equal(h, h0) and torch.equal(gw, gw0)
