@@ -39,7 +39,8 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-@pytest.mark.parametrize("k,add_self", [(5, False), (10, False), (25, True), (1, False), (None, False), (None, True)])
+@pytest.mark.parametrize("k,add_self", [(5, False), (10, False), (25, True), (1, False), (None, False), (None, True),
+                                        (32, False), (40, True), (64, False)])
 def test_sampler_bit_exact(ops, k, add_self):
     rng = np.random.default_rng(3)
     n = 3000
@@ -402,3 +403,26 @@ def test_encoder_tensor_core_repeatable(ops):
         gw = torch.full((d_out, k_in), float("nan"), device="cuda")
         ops.encoder_wgrad_tc(x, h0, gh, act, gw)
         assert torch.equal(h, h0) and torch.equal(gw, gw0)
+
+
+def test_sampler_rejects_unsupported_fanout(ops):
+    """k > 64 is outside the kernel's register-resident Floyd set: an error code, not a wrong answer."""
+    rowptr = dev(np.array([0, 2], dtype=np.int64)); col = dev(np.array([0, 0], dtype=np.int32))
+    with pytest.raises(RuntimeError, match="not supported"):
+        ops.sample_csr(rowptr, col, 1, dev(np.zeros(1, np.int32)), 65)
+
+
+def test_degenerate_batches(ops):
+    """Edge cases the reference hits with tiny graphs: a single target, rows without neighbours (the reference
+    divides 0/0 -> NaN, aggregators.py:60-61; documented deviation: zeros), an empty frontier."""
+    table = ops.empty_rows(5, 12, "cuda"); table.copy_(torch.arange(60, device="cuda", dtype=torch.float32).view(5, 12))
+    idx = dev(np.array([[3, -1, -1]], dtype=np.int32)); cnt = dev(np.array([1], dtype=np.int32))
+    out = ops.empty_rows(1, 24, "cuda", zero=True)
+    ops.gather_mean_fwd(table, 12, idx, cnt, out, neigh_off=12, self_ids=dev(np.array([4], dtype=np.int32)))
+    assert torch.equal(out[0, :12], table[4]) and torch.equal(out[0, 12:], table[3])
+    cnt0 = dev(np.array([0], dtype=np.int32))
+    ops.gather_mean_fwd(table, 12, idx, cnt0, out, neigh_off=12, self_ids=None)
+    assert torch.equal(out[0, 12:], torch.zeros(12, device="cuda"))
+    empty_ids = torch.zeros(0, dtype=torch.int32, device="cuda")
+    i0, c0 = ops.sample_csr(dev(np.array([0, 1], dtype=np.int64)), dev(np.array([0], dtype=np.int32)), 1, empty_ids, 5)
+    assert i0.shape == (0, 5) and c0.shape == (0,)
