@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--graph", default="uniform", choices=["uniform", "rmat"],
                     help="uniform: default_rng(1) pairs (SURVEY s8d, the judged line); rmat: heavy-tailed variant "
                          "(a,b,c = 0.57,0.19,0.19, same node count and pair count, every node >= 1 edge) for hub stress")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "a2a"],
+                    help="products workload: peer = remote rows read over NVLink inside the kernels (symmetric memory); "
+                         "a2a = NCCL all-to-all round trip per lookup")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
     return ap.parse_args()
@@ -539,13 +542,14 @@ def run_products(args):
     if world > 1:
         dist.all_reduce(deg_max, op=dist.ReduceOp.MAX)
     ex = sharded.OwnerExchange(rank, world)
-    graph = sharded.ShardedCSR(rowptr, col, n, int(deg_max.item()), ex, dev)
+    peer = args.exchange == "peer"
+    graph = sharded.ShardedCSR(rowptr, col, n, int(deg_max.item()), ex, dev, peer=peer)
     entries_local = int(col.shape[0])
     del rowptr, col
     gen = torch.Generator(device=dev)
     gen.manual_seed(2)
     full = torch.randn(n, feat, device=dev, generator=gen)      # 0.96 GB transient; each rank keeps its rows
-    feats = sharded.ShardedFeatures(full[rank::world].contiguous(), n, exchange=ex)
+    feats = sharded.ShardedFeatures(full[rank::world].contiguous(), n, exchange=ex, peer=peer)
     del full
     labels_np = np.random.default_rng(2).integers(0, classes, (n, 1)).astype(np.int64)
     torch.manual_seed(2)
@@ -600,14 +604,15 @@ def run_products(args):
                                        "%d-d fp32 features, %d classes, 3-layer SAGE-mean concat, hidden %d, fan-out "
                                        "15/10/5 from the targets outward, SGD" % (n, pairs, feat, classes, args.hidden),
                            "batch_per_gpu": B, "global_batch": B * world,
-                           "parallelism": "feature table + CSR partitioned by owner = id %% %d; NCCL all-to-all per lookup; "
-                                          "all-reduce of weight grads" % world,
+                           "parallelism": "feature table + CSR partitioned by owner = id %% %d; %s; all-reduce of weight grads" % (
+                               world, "remote rows read over NVLink peer memory inside the gather / sampler kernels"
+                               if peer else "NCCL all-to-all per lookup"),
                            "l2_policy": "inputs larger than L2: fresh random targets every step", "lr": args.lr,
                            "csr_entries_rank0": entries_local, "build_s": build_s},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 4,
                         "api": "the reference's loop (model.py:245-250) on the drop-in modules with host ids/labels"},
                 "gpu_launches": ops.LAUNCHES[0] - launches0, "clocks": clocks.summary(),
-                "roofline": {"kernel": "all-to-all exchange (ids + feature rows + sampled tiles), rank 0 send side",
+                "roofline": None if peer else {"kernel": "all-to-all exchange (ids + feature rows + sampled tiles), rank 0 send side",
                              "bound": "nvlink", "achieved": wire, "peak": 900.0, "unit": "GB/s", "frac": wire / 900.0,
                              "traffic": None, "bytes_sent_per_step_rank0": sent,
                              "note": "op-by-op path: the step is launch/sync-bound, not wire-bound (one host sync per lookup)"},

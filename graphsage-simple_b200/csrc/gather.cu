@@ -9,6 +9,25 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 
+// Where feature row `id` lives.  Plain: one table.  Partitioned: node v is owned by rank
+// v % world as local row v / world, and `peers[q]` is rank q's shard mapped into this process (symmetric
+// memory), so a remote row is read straight over NVLink by the gathering warp -- the exchange step of the
+// partitioned path fused into the gather itself, no all-to-all, no staging buffer.
+struct TableRef {
+    const float* table;             // world == 1
+    const float* const* peers;      // world > 1
+    int world, shift;               // shift = log2(world) when world is a power of two, else -1
+};
+
+template <bool PEER>
+__device__ __forceinline__ const float* row_ptr(const TableRef& t, int id, int64_t ld) {
+    if (!PEER) return t.table + (int64_t)id * ld;
+    const unsigned u = (unsigned)id;
+    const unsigned owner = t.shift >= 0 ? (u & (unsigned)(t.world - 1)) : (u % (unsigned)t.world);
+    const unsigned local = t.shift >= 0 ? (u >> t.shift) : (u / (unsigned)t.world);
+    return t.peers[owner] + (int64_t)local * ld;       // 8-byte pointer table, L1-resident
+}
+
 // Load 4 consecutive floats of a row whose base is 16-B aligned; columns >= dim read as 0.
 __device__ __forceinline__ float4 load_chunk(const float* __restrict__ row, int c4, int dim) {
     const int col = c4 * 4;
@@ -41,9 +60,9 @@ __device__ __forceinline__ void store_chunk(float* __restrict__ dst_row, int c4,
 // warp-wide load is one contiguous 512-byte run of the neighbour's row (4 full 128-B lines).
 // CH chunks per lane are kept in registers and NB neighbours are in flight at once, i.e.
 // CH*NB independent 128-bit loads per lane, which is what hides HBM latency here.
-template <int CH, int NB>
+template <int CH, int NB, bool PEER>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
-gather_mean_kernel(const float* __restrict__ table, int64_t ld_table, int dim,
+gather_mean_kernel(const TableRef table, int64_t ld_table, int dim,
                    const int32_t* __restrict__ idx, const int32_t* __restrict__ cnt, int width,
                    const int32_t* __restrict__ self_ids, int n_max, const int32_t* __restrict__ n_dev,
                    float* __restrict__ out, int64_t ld_out, int neigh_off, int out_align) {
@@ -60,7 +79,7 @@ gather_mean_kernel(const float* __restrict__ table, int64_t ld_table, int dim,
     const int32_t* irow = idx + (int64_t)row * width;
 
     if (self_ids != nullptr) {          // bit-exact copy of the node's own row (encoders.py:53)
-        const float* srow = table + (int64_t)self_ids[row] * ld_table;
+        const float* srow = row_ptr<PEER>(table, self_ids[row], ld_table);
         for (int c4 = lane; c4 < nchunks; c4 += 32) store_chunk(orow, c4, dim, 4, load_chunk(srow, c4, dim));
     }
     for (int c0 = 0; c0 < nchunks; c0 += 32 * CH) {
@@ -75,7 +94,7 @@ gather_mean_kernel(const float* __restrict__ table, int64_t ld_table, int dim,
                 float4 v[NB][CH];
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    const float* nrow = table + (int64_t)__shfl_sync(0xffffffffu, my, j + b) * ld_table;
+                    const float* nrow = row_ptr<PEER>(table, __shfl_sync(0xffffffffu, my, j + b), ld_table);
 #pragma unroll
                     for (int u = 0; u < CH; ++u) {
                         const int c4 = c0 + u * 32 + lane;
@@ -91,7 +110,7 @@ gather_mean_kernel(const float* __restrict__ table, int64_t ld_table, int dim,
                     }
             }
             for (; j < lim; ++j) {
-                const float* nrow = table + (int64_t)__shfl_sync(0xffffffffu, my, j) * ld_table;
+                const float* nrow = row_ptr<PEER>(table, __shfl_sync(0xffffffffu, my, j), ld_table);
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
                     const int c4 = c0 + u * 32 + lane;
@@ -114,8 +133,9 @@ gather_mean_kernel(const float* __restrict__ table, int64_t ld_table, int dim,
     }
 }
 
+template <bool PEER>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-gather_rows_kernel(const float* __restrict__ table, int64_t ld_table, int dim,
+gather_rows_kernel(const TableRef table, int64_t ld_table, int dim,
                    const int32_t* __restrict__ ids, int n_max, const int32_t* __restrict__ n_dev,
                    float* __restrict__ out, int64_t ld_out) {
     const int n = gs_row_count(n_max, n_dev);
@@ -123,7 +143,7 @@ gather_rows_kernel(const float* __restrict__ table, int64_t ld_table, int dim,
     const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (row >= n) return;
     const int nchunks = (dim + 3) >> 2;
-    const float* srow = table + (int64_t)ids[row] * ld_table;
+    const float* srow = row_ptr<PEER>(table, ids[row], ld_table);
     float* orow = out + (int64_t)row * ld_out;
     for (int c4 = lane; c4 < nchunks; c4 += 32) store_chunk(orow, c4, dim, 4, load_chunk(srow, c4, dim));
 }
@@ -183,14 +203,18 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
 
 }  // namespace
 
-extern "C" int gs_gather_mean_fwd(const float* table, int64_t ld_table, int32_t dim,
-                                  const int32_t* idx, const int32_t* cnt, int32_t width,
-                                  const int32_t* self_ids, int32_t n_max, const int32_t* n_dev,
-                                  float* out, int64_t ld_out, int32_t neigh_off, void* stream) {
-    if (!table || !idx || !cnt || !out || dim <= 0 || width <= 0 || n_max < 0 || neigh_off < 0) return GS_EINVAL;
-    if (!gs_aligned16(table) || !gs_aligned16(out) || (ld_table & 3) || (ld_out & 3)) return GS_EALIGN;
-    if (ld_table < dim || ld_out < neigh_off + dim) return GS_EINVAL;
-    if (n_max == 0) return GS_OK;
+namespace {
+
+TableRef peer_ref(const float* const* tables, int world) {
+    int shift = -1;
+    for (int b = 0; b < 5; ++b) if ((1 << b) == world) shift = b;
+    return TableRef{nullptr, tables, world, shift};
+}
+
+int launch_gather_mean(const TableRef& table, bool peer, int64_t ld_table, int32_t dim,
+                       const int32_t* idx, const int32_t* cnt, int32_t width,
+                       const int32_t* self_ids, int32_t n_max, const int32_t* n_dev,
+                       float* out, int64_t ld_out, int32_t neigh_off, void* stream) {
     const int align = (neigh_off & 3) == 0 ? 4 : ((neigh_off & 1) == 0 ? 2 : 1);
     const int nchunks = (dim + 3) / 4;
     // Register budget of an SM (64 K): the gather must leave room for a co-resident tcgen05 GEMM CTA
@@ -215,19 +239,49 @@ extern "C" int gs_gather_mean_fwd(const float* table, int64_t ld_table, int32_t 
     if (nblocks > GS_NUM_SMS * bps) nblocks = GS_NUM_SMS * bps;
     const dim3 grid(nblocks), block(wpb * 32);
     cudaStream_t s = (cudaStream_t)stream;
-#define GS_GM(CH, NB) if (carve == 1) GS_PREFER_SMEM((gather_mean_kernel<CH, NB>)); \
-        else if (carve > 1) { static bool d__ = false; if (!d__) { cudaFuncSetAttribute((gather_mean_kernel<CH, NB>), \
-            cudaFuncAttributePreferredSharedMemoryCarveout, carve); d__ = true; } } \
-        gather_mean_kernel<CH, NB><<<grid, block, 0, s>>>(table, ld_table, dim, idx, cnt, width, \
-        self_ids, n_max, n_dev, out, ld_out, neigh_off, align)
+#define GS_GM1(CH, NB, P) do { \
+        static bool d__ = false; \
+        if (!d__ && carve) { cudaFuncSetAttribute((gather_mean_kernel<CH, NB, P>), cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                                  carve == 1 ? (int)cudaSharedmemCarveoutMaxShared : carve); d__ = true; } \
+        gather_mean_kernel<CH, NB, P><<<grid, block, 0, s>>>(table, ld_table, dim, idx, cnt, width, \
+            self_ids, n_max, n_dev, out, ld_out, neigh_off, align); } while (0)
+#define GS_GM(CH, NB) do { if (peer) GS_GM1(CH, NB, true); else GS_GM1(CH, NB, false); } while (0)
     if (nchunks <= 32) { GS_GM(1, 8); }
     else if (nchunks <= 64) { GS_GM(2, 4); }
     else if (nchunks <= 96) { GS_GM(3, 4); }
     else if (nchunks <= 128) { GS_GM(4, 2); }
     else { GS_GM(5, 2); }
 #undef GS_GM
+#undef GS_GM1
     GS_LAUNCH_CHECK();
     return GS_OK;
+}
+
+}  // namespace
+
+extern "C" int gs_gather_mean_fwd(const float* table, int64_t ld_table, int32_t dim,
+                                  const int32_t* idx, const int32_t* cnt, int32_t width,
+                                  const int32_t* self_ids, int32_t n_max, const int32_t* n_dev,
+                                  float* out, int64_t ld_out, int32_t neigh_off, void* stream) {
+    if (!table || !idx || !cnt || !out || dim <= 0 || width <= 0 || n_max < 0 || neigh_off < 0) return GS_EINVAL;
+    if (!gs_aligned16(table) || !gs_aligned16(out) || (ld_table & 3) || (ld_out & 3)) return GS_EALIGN;
+    if (ld_table < dim || ld_out < neigh_off + dim) return GS_EINVAL;
+    if (n_max == 0) return GS_OK;
+    return launch_gather_mean(TableRef{table, nullptr, 1, 0}, false, ld_table, dim, idx, cnt, width, self_ids, n_max, n_dev,
+                              out, ld_out, neigh_off, stream);
+}
+
+extern "C" int gs_gather_mean_fwd_peer(const float* const* tables, int32_t world, int64_t ld_table, int32_t dim,
+                                       const int32_t* idx, const int32_t* cnt, int32_t width,
+                                       const int32_t* self_ids, int32_t n_max, const int32_t* n_dev,
+                                       float* out, int64_t ld_out, int32_t neigh_off, void* stream) {
+    if (!tables || !idx || !cnt || !out || dim <= 0 || width <= 0 || n_max < 0 || neigh_off < 0) return GS_EINVAL;
+    if (world < 1 || world > 16) return GS_ENOSUP;
+    if (!gs_aligned16(out) || (ld_table & 3) || (ld_out & 3)) return GS_EALIGN;
+    if (ld_table < dim || ld_out < neigh_off + dim) return GS_EINVAL;
+    if (n_max == 0) return GS_OK;
+    return launch_gather_mean(peer_ref(tables, world), true, ld_table, dim, idx, cnt, width, self_ids, n_max, n_dev,
+                              out, ld_out, neigh_off, stream);
 }
 
 extern "C" int gs_gather_rows(const float* table, int64_t ld_table, int32_t dim, const int32_t* ids,
@@ -236,10 +290,24 @@ extern "C" int gs_gather_rows(const float* table, int64_t ld_table, int32_t dim,
     if (!table || !ids || !out || dim <= 0 || n_max < 0) return GS_EINVAL;
     if (!gs_aligned16(table) || !gs_aligned16(out) || (ld_table & 3) || (ld_out & 3)) return GS_EALIGN;
     if (ld_table < dim || ld_out < dim) return GS_EINVAL;
+    GS_PREFER_SMEM(gather_rows_kernel<false>);
+    gather_rows_kernel<false><<<(n_max + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        TableRef{table, nullptr, 1, 0}, ld_table, dim, ids, n_max, n_dev, out, ld_out);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+extern "C" int gs_gather_rows_peer(const float* const* tables, int32_t world, int64_t ld_table, int32_t dim,
+                                   const int32_t* ids, int32_t n_max, const int32_t* n_dev, float* out, int64_t ld_out,
+                                   void* stream) {
     if (n_max == 0) return GS_OK;
-    GS_PREFER_SMEM(gather_rows_kernel);
-    gather_rows_kernel<<<(n_max + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-        table, ld_table, dim, ids, n_max, n_dev, out, ld_out);
+    if (!tables || !ids || !out || dim <= 0 || n_max < 0) return GS_EINVAL;
+    if (world < 1 || world > 16) return GS_ENOSUP;
+    if (!gs_aligned16(out) || (ld_table & 3) || (ld_out & 3)) return GS_EALIGN;
+    if (ld_table < dim || ld_out < dim) return GS_EINVAL;
+    GS_PREFER_SMEM(gather_rows_kernel<true>);
+    gather_rows_kernel<true><<<(n_max + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        peer_ref(tables, world), ld_table, dim, ids, n_max, n_dev, out, ld_out);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }

@@ -94,8 +94,18 @@ sample_csr_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
 // specification (and bit-identical output) as the thread-per-row kernel above.
 constexpr int kWarpRows = 8;      // warps (rows) per block
 
+// Partitioned CSR: node v's neighbour list lives on rank v % world as local row v / world of that
+// rank's (rowptr, col); `rowptrs[q]` / `cols[q]` are rank q's arrays mapped into this process (symmetric memory), so
+// the sampling warp reads a remote adjacency row straight over NVLink.  Draws are keyed on the GLOBAL id.
+struct CsrPeers {
+    const int64_t* const* rowptrs;
+    const int32_t* const* cols;
+    int world, shift;
+};
+
+template <bool PEER>
 __global__ void __launch_bounds__(kWarpRows * 32)
-sample_csr_warp_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+sample_csr_warp_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const CsrPeers peers,
                        const int32_t* __restrict__ nodes, int n_max, const int32_t* __restrict__ n_dev,
                        int k, int width, int add_self, uint32_t seed_lo, uint32_t seed_hi,
                        int64_t step_imm, const int64_t* __restrict__ step_dev,
@@ -112,8 +122,16 @@ sample_csr_warp_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
         return;
     }
     const int32_t v = nodes[i];
-    const int64_t base = rowptr[v];
-    const int deg = (int)(rowptr[v + 1] - base);
+    int r = v;
+    if (PEER) {
+        const unsigned u = (unsigned)v;
+        const unsigned owner = peers.shift >= 0 ? (u & (unsigned)(peers.world - 1)) : (u % (unsigned)peers.world);
+        r = (int)(peers.shift >= 0 ? (u >> peers.shift) : (u / (unsigned)peers.world));
+        rowptr = peers.rowptrs[owner];
+        col = peers.cols[owner];
+    }
+    const int64_t base = rowptr[r];
+    const int deg = (int)(rowptr[r + 1] - base);
     int c;
     bool has_self = false;
     if (k < 0 || deg <= k) {
@@ -293,16 +311,37 @@ extern "C" int gs_sample_csr(const int64_t* rowptr, const int32_t* col, int32_t 
     if (k >= 0 && width < k + (add_self ? 1 : 0)) return GS_EINVAL;
     if (n_max == 0) return GS_OK;
     if (k <= 32) {
-        GS_PREFER_SMEM(sample_csr_warp_kernel);
-        sample_csr_warp_kernel<<<(n_max + kWarpRows - 1) / kWarpRows, kWarpRows * 32, 0, (cudaStream_t)stream>>>(
-            rowptr, col, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed, (uint32_t)(seed >> 32),
-            step, step_dev, tag_head, tag_tail, n_head, idx, cnt);
+        GS_PREFER_SMEM(sample_csr_warp_kernel<false>);
+        sample_csr_warp_kernel<false><<<(n_max + kWarpRows - 1) / kWarpRows, kWarpRows * 32, 0, (cudaStream_t)stream>>>(
+            rowptr, col, CsrPeers{nullptr, nullptr, 1, 0}, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed,
+            (uint32_t)(seed >> 32), step, step_dev, tag_head, tag_tail, n_head, idx, cnt);
     } else {
         const int threads = 128;
         sample_csr_kernel<<<(n_max + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
             rowptr, col, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed, (uint32_t)(seed >> 32),
             step, step_dev, tag_head, tag_tail, n_head, idx, cnt);
     }
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+extern "C" int gs_sample_csr_peer(const int64_t* const* rowptrs, const int32_t* const* cols, int32_t world,
+                                  int32_t num_nodes, const int32_t* nodes, int32_t n_max, const int32_t* n_dev,
+                                  int32_t k, int32_t width, int32_t add_self,
+                                  uint64_t seed, int64_t step, const int64_t* step_dev,
+                                  uint32_t tag_head, uint32_t tag_tail, int32_t n_head,
+                                  int32_t* idx, int32_t* cnt, void* stream) {
+    (void)num_nodes;
+    if (n_max == 0) return GS_OK;
+    if (!rowptrs || !cols || !nodes || !idx || !cnt || n_max < 0 || width <= 0) return GS_EINVAL;
+    if (world < 1 || world > 16 || k > 32) return GS_ENOSUP;
+    if (k >= 0 && width < k + (add_self ? 1 : 0)) return GS_EINVAL;
+    int shift = -1;
+    for (int b = 0; b < 5; ++b) if ((1 << b) == world) shift = b;
+    GS_PREFER_SMEM(sample_csr_warp_kernel<true>);
+    sample_csr_warp_kernel<true><<<(n_max + kWarpRows - 1) / kWarpRows, kWarpRows * 32, 0, (cudaStream_t)stream>>>(
+        nullptr, nullptr, CsrPeers{rowptrs, cols, world, shift}, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed,
+        (uint32_t)(seed >> 32), step, step_dev, tag_head, tag_tail, n_head, idx, cnt);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }

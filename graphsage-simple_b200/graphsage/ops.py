@@ -322,6 +322,55 @@ def allreduce_sgd(p, g, lr, stage_ptrs, flag_ptrs, rank, world, state):
     return p
 
 
+def gather_rows_peer(table_ptrs, world, ld, dim, ids, out, n_dev=None):
+    """gs_gather_rows over a table partitioned by owner = id % world, shards read through peer memory."""
+    lib = N.load()
+    N.require_cuda(table_ptrs, ids, out)
+    N.check(lib.gs_gather_rows_peer(N.ptr(table_ptrs), int(world), int(ld), int(dim), N.ptr(ids), ids.shape[0], N.ptr(n_dev),
+                                    N.ptr(out), out.stride(0), N.stream()), "gs_gather_rows_peer")
+    LAUNCHES[0] += 1
+    return out
+
+
+def gather_mean_fwd_peer(table_ptrs, world, ld, dim, idx, cnt, out, neigh_off=0, self_ids=None, n_dev=None):
+    lib = N.load()
+    N.require_cuda(table_ptrs, idx, cnt, out)
+    n_max, width = idx.shape
+    N.check(lib.gs_gather_mean_fwd_peer(N.ptr(table_ptrs), int(world), int(ld), int(dim), N.ptr(idx), N.ptr(cnt), width,
+                                        N.ptr(self_ids), n_max, N.ptr(n_dev), N.ptr(out), out.stride(0), int(neigh_off),
+                                        N.stream()), "gs_gather_mean_fwd_peer")
+    LAUNCHES[0] += 1
+    return out
+
+
+def sample_csr_peer(rowptr_ptrs, col_ptrs, world, num_nodes, nodes, k, add_self=False, seed=0, step=0, tag_head=0,
+                    tag_tail=None, n_head=None, n_dev=None, step_dev=None, width=None, idx=None, cnt=None):
+    """gs_sample_csr over a CSR partitioned by owner = id % world, rows read through peer memory."""
+    lib = N.load()
+    N.require_cuda(rowptr_ptrs, col_ptrs, nodes)
+    n_max = nodes.shape[0]
+    kk = -1 if k is None else int(k)
+    if width is None:
+        if kk < 0:
+            raise ValueError("width must be given for take-all sampling")
+        width = kk + (1 if add_self else 0)
+    width = max(int(width), 1)
+    if idx is None:
+        idx = torch.empty((max(n_max, 1), width), device=nodes.device, dtype=torch.int32)[:n_max]
+    if cnt is None:
+        cnt = torch.empty((max(n_max, 1),), device=nodes.device, dtype=torch.int32)[:n_max]
+    if tag_tail is None:
+        tag_tail = tag_head
+    if n_head is None:
+        n_head = n_max
+    N.check(lib.gs_sample_csr_peer(N.ptr(rowptr_ptrs), N.ptr(col_ptrs), int(world), int(num_nodes), N.ptr(nodes), n_max,
+                                   N.ptr(n_dev), kk, width, int(bool(add_self)), int(seed) & (2 ** 64 - 1), int(step),
+                                   N.ptr(step_dev), int(tag_head), int(tag_tail), int(n_head), N.ptr(idx), N.ptr(cnt),
+                                   N.stream()), "gs_sample_csr_peer")
+    LAUNCHES[0] += 1
+    return idx, cnt
+
+
 def advance_step(step_dev):
     N.check(N.load().gs_advance_step(N.ptr(step_dev), N.stream()), "gs_advance_step")
     LAUNCHES[0] += 1

@@ -27,6 +27,31 @@ def _round4(x):
     return (int(x) + 3) // 4 * 4
 
 
+def peer_mapped(t, group=None):
+    """Put tensor ``t`` (this rank's shard; sizes may differ between ranks) into symmetric memory and
+    return ``(local, ptrs)``: ``local`` aliases the symmetric buffer with t's shape and values, ``ptrs`` is an
+    int64 CUDA tensor [world] holding every rank's buffer as mapped into THIS process -- what the
+    ``*_peer`` kernels take.  Collective: every rank of the group must call it.  Without a process
+    group (world 1) the tensor itself is used."""
+    on = dist.is_available() and dist.is_initialized()
+    t = t.contiguous()
+    if not on or dist.get_world_size(group) == 1:
+        return t, torch.tensor([t.data_ptr()], dtype=torch.int64, device=t.device)
+    import torch.distributed._symmetric_memory as symm
+    group = group if group is not None else dist.group.WORLD
+    n = torch.tensor([t.numel()], device=t.device, dtype=torch.int64)
+    dist.all_reduce(n, op=dist.ReduceOp.MAX, group=group)
+    buf = symm.empty(max(int(n.item()), 1), dtype=t.dtype, device=t.device)
+    buf[:t.numel()].copy_(t.reshape(-1))
+    handle = symm.rendezvous(buf, group)
+    ptrs = torch.tensor([int(p) for p in handle.buffer_ptrs], dtype=torch.int64, device=t.device)
+    torch.cuda.synchronize(t.device)
+    dist.barrier(group)                      # every shard is complete before anyone reads it remotely
+    local = buf[:t.numel()].view(t.shape)
+    local._gs_symm_handle = handle           # keep the mapping alive as long as the view
+    return local, ptrs
+
+
 class _Plan:
     __slots__ = ("perm", "send_splits", "recv_splits", "recv_ids", "n")
 
@@ -96,9 +121,12 @@ class ShardedFeatures(nn.Module):
     FloatTensor of feature values") over a table whose row ``v`` lives on rank ``v % world`` as
     local row ``v // world``.  Frozen, like the reference's table (model.py:214-215)."""
 
-    def __init__(self, local_rows, num_nodes, rank=None, world=None, group=None, exchange=None):
+    def __init__(self, local_rows, num_nodes, rank=None, world=None, group=None, exchange=None, peer=False):
+        """``peer=True``: the shards are mapped into every rank (symmetric memory) and a lookup is ONE kernel
+        that reads remote rows over NVLink (gs_gather_rows_peer) instead of the all-to-all round trip."""
         super().__init__()
         self.ex = exchange if exchange is not None else OwnerExchange(rank, world, group)
+        self.peer = bool(peer)
         self.num_nodes = int(num_nodes)
         self.dim = int(local_rows.shape[1])
         self.ld = _round4(self.dim)
@@ -107,6 +135,9 @@ class ShardedFeatures(nn.Module):
             buf = torch.zeros((t.shape[0], self.ld), dtype=torch.float32, device=t.device)
             buf[:, :self.dim] = t
             t = buf
+        self.table_ptrs = None
+        if self.peer:
+            t, self.table_ptrs = peer_mapped(t, self.ex.group)
         self.register_buffer("table", t, persistent=False)
 
     @staticmethod
@@ -122,6 +153,11 @@ class ShardedFeatures(nn.Module):
 
     def forward(self, ids):
         ids32 = ops.as_ids(ids, self.table.device)
+        if self.peer:
+            n = ids32.shape[0]
+            out = torch.empty((max(n, 1), self.ld), device=self.table.device, dtype=torch.float32)[:n]
+            ops.gather_rows_peer(self.table_ptrs, self.ex.world, self.ld, self.ld, ids32, out)
+            return out[:, :self.dim]
         plan = self.ex.route(ids32, emit_local=True)
         rows = self.ex.reply(plan, self._local_rows(plan.recv_ids))
         return rows[:, :self.dim]
@@ -132,8 +168,11 @@ class ShardedCSR:
     (``col``); ``rowptr`` stays full length (8 B per node, rows of other ranks are empty) so the sampler
     kernel is indexed by global id unchanged.  ``sample`` answers the same call as CSRGraph.sample."""
 
-    def __init__(self, rowptr_local, col_local, num_nodes, max_degree, exchange, device="cuda"):
+    def __init__(self, rowptr_local, col_local, num_nodes, max_degree, exchange, device="cuda", peer=False):
+        """``peer=True``: every rank's (compact rowptr, col) is mapped into every rank and sampling is ONE
+        kernel reading remote adjacency rows over NVLink (gs_sample_csr_peer)."""
         self.ex = exchange
+        self.peer = bool(peer)
         self.num_nodes = int(num_nodes)
         self.max_degree = int(max_degree)
         self.device = torch.device(device)
@@ -141,9 +180,16 @@ class ShardedCSR:
         col = np.ascontiguousarray(col_local, dtype=np.int32)
         self.col = torch.as_tensor(col if col.size else np.zeros(1, np.int32)).to(self.device)
         self.num_entries = int(col.shape[0])
+        self.rowptr_ptrs = self.col_ptrs = None
+        if self.peer:
+            rp = np.ascontiguousarray(rowptr_local, dtype=np.int64)
+            w, r = self.ex.world, self.ex.rank
+            compact = np.concatenate([rp[r:self.num_nodes:w], rp[-1:]])          # owned rows only: local row = v // world
+            self._rp_local, self.rowptr_ptrs = peer_mapped(torch.from_numpy(compact).to(self.device), self.ex.group)
+            self._col_local, self.col_ptrs = peer_mapped(self.col, self.ex.group)
 
     @classmethod
-    def from_global(cls, rowptr, col, rank, world, device="cuda", exchange=None):
+    def from_global(cls, rowptr, col, rank, world, device="cuda", exchange=None, peer=False):
         """Keep the rows v % world == rank of a full CSR (host arrays)."""
         rowptr = np.asarray(rowptr, dtype=np.int64)
         col = np.asarray(col)
@@ -155,7 +201,7 @@ class ShardedCSR:
         np.cumsum(deg_local, out=rp[1:])
         keep = np.repeat(mine, deg)
         ex = exchange if exchange is not None else OwnerExchange(rank, world)
-        return cls(rp, col[keep].astype(np.int32), n, int(deg.max()) if n else 0, ex, device)
+        return cls(rp, col[keep].astype(np.int32), n, int(deg.max()) if n else 0, ex, device, peer=peer)
 
     def _local_sample(self, ids, k, add_self, seed, step, tag, width):
         return ops.sample_csr(self.rowptr, self.col, self.num_nodes, ids, k, add_self=add_self, seed=seed,
@@ -165,6 +211,9 @@ class ShardedCSR:
         if width is None:
             width = (k if k is not None else self.max_degree) + (1 if add_self else 0)
         width = max(int(width), 1)
+        if self.peer:
+            return ops.sample_csr_peer(self.rowptr_ptrs, self.col_ptrs, self.ex.world, self.num_nodes, ids, k,
+                                       add_self=add_self, seed=seed, step=step, tag_head=tag, width=width)
         plan = self.ex.route(ids, emit_local=False)
         idx, cnt = self._local_sample(plan.recv_ids, k, add_self, seed, step, tag, width)
         ld = _round4(width + 1)

@@ -235,6 +235,28 @@ GS_API int gs_bucket_by_owner(const int32_t* ids, int32_t n_max, const int32_t* 
                        int32_t emit_local, int32_t* scratch, int32_t* send_ids, int32_t* perm,
                        int32_t* counts, void* stream);
 
+/* ---- partitioned table / CSR read through peer memory (NVLink) -----------------------------------
+ * Same contracts as gs_gather_rows, gs_gather_mean_fwd and gs_sample_csr (k <= 32 or take-all) for
+ * a feature table / CSR partitioned by owner = id % world: node v is local row v / world of rank
+ * v % world.  tables / rowptrs / cols are DEVICE arrays of `world` pointers, entry q = rank q's shard
+ * as mapped into this process (CUDA IPC / symmetric memory); ld_table is common to all shards and
+ * rank q's rowptr has (its row count + 1) entries into its own col.  The exchange of the partitioned
+ * path is thereby fused into the kernels: remote rows are read over NVLink by the
+ * warp that consumes them; no all-to-all, no staging, no host synchronisation.               */
+GS_API int gs_gather_rows_peer(const float* const* tables, int32_t world, int64_t ld_table, int32_t dim,
+                        const int32_t* ids, int32_t n_max, const int32_t* n_dev, float* out, int64_t ld_out,
+                        void* stream);
+GS_API int gs_gather_mean_fwd_peer(const float* const* tables, int32_t world, int64_t ld_table, int32_t dim,
+                            const int32_t* idx, const int32_t* cnt, int32_t width,
+                            const int32_t* self_ids, int32_t n_max, const int32_t* n_dev,
+                            float* out, int64_t ld_out, int32_t neigh_off, void* stream);
+GS_API int gs_sample_csr_peer(const int64_t* const* rowptrs, const int32_t* const* cols, int32_t world,
+                       int32_t num_nodes, const int32_t* nodes, int32_t n_max, const int32_t* n_dev,
+                       int32_t k, int32_t width, int32_t add_self,
+                       uint64_t seed, int64_t step, const int64_t* step_dev,
+                       uint32_t tag_head, uint32_t tag_tail, int32_t n_head,
+                       int32_t* idx, int32_t* cnt, void* stream);
+
 /* Small device-side helpers used to keep a training step free of host round trips.       */
 GS_API int gs_advance_step(int64_t* step_dev, void* stream);                    /* ++*step_dev   */
 

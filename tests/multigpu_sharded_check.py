@@ -30,9 +30,8 @@ def relerr(a, b):
 
 
 def main():
-    from graphsage import ops, sampling, sharded
+    from graphsage import sharded
     from graphsage.graph import CSRGraph
-    from graphsage.model import build_sage
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -50,9 +49,24 @@ def main():
     table = torch.from_numpy(rng.standard_normal((n, f)).astype(np.float32)).to(dev)
     labels = rng.integers(0, c, (n, 1)).astype(np.int64)
 
+    for peer in (False, True):
+        check_mode(peer, sharded, full, rowptr, col, table, labels, n, f, c, rank, world, dev)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        print("SHARDED-CHECK OK world=%d (all-to-all and peer-memory lookups)" % world)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def check_mode(peer, sharded, full, rowptr, col, table, labels, n, f, c, rank, world, dev):
+    """peer=False: NCCL all-to-all round trips; peer=True: remote rows read over NVLink inside the kernels."""
+    from graphsage import sampling
+    from graphsage.model import build_sage
     ex = sharded.OwnerExchange(rank, world)
-    feats = sharded.ShardedFeatures(sharded.ShardedFeatures.shard_of(table, rank, world).contiguous(), n, exchange=ex)
-    graph = sharded.ShardedCSR.from_global(rowptr, col, rank, world, device=dev, exchange=ex)
+    feats = sharded.ShardedFeatures(sharded.ShardedFeatures.shard_of(table, rank, world).contiguous(), n, exchange=ex,
+                                    peer=peer)
+    graph = sharded.ShardedCSR.from_global(rowptr, col, rank, world, device=dev, exchange=ex, peer=peer)
 
     # 1 + 2: lookups (every rank asks for different, duplicate-containing ids; one rank asks for nothing)
     my = np.random.default_rng(50 + rank)
@@ -101,13 +115,9 @@ def main():
     run(model_l, encs_l, split=False)
     for ps, pl in zip(model_s.parameters(), model_l.parameters()):
         e = relerr(ps.detach(), pl.detach())
-        assert e < 1e-5, "weights after 3 partitioned steps differ from the single-rank run: %g" % e
-    if world > 1:
-        dist.barrier()
-    if rank == 0:
-        print("SHARDED-CHECK OK world=%d bytes_sent_rank0=%d" % (world, ex.bytes_sent))
-    if world > 1:
-        dist.destroy_process_group()
+        assert e < 1e-5, "weights after 3 partitioned steps differ from the single-rank run: %g (peer=%s)" % (e, peer)
+    if not peer:
+        assert world == 1 or ex.bytes_sent > 0
 
 
 if __name__ == "__main__":
