@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--graph", default="uniform", choices=["uniform", "rmat"],
                     help="uniform: default_rng(1) pairs (SURVEY s8d, the judged line); rmat: heavy-tailed variant "
                          "(a,b,c = 0.57,0.19,0.19, same node count and pair count, every node >= 1 edge) for hub stress")
+    ap.add_argument("--partitioned", action="store_true",
+                    help="reddit workload on N GPUs with the feature table AND the CSR partitioned by owner = id %% N and read "
+                         "through NVLink peer memory by the fused engine's gather / sampler kernels (instead of replicas)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "a2a"],
                     help="products workload: peer = remote rows read over NVLink inside the kernels (symmetric memory); "
                          "a2a = NCCL all-to-all round trip per lookup")
@@ -215,8 +218,10 @@ def workload_config(args, batch):
                         "%d (hop-1), SGD" % (args.nodes, args.pairs, args.feat, args.classes, args.hidden,
                                             args.hidden, args.k2, args.k1),
             "batch_per_gpu": batch, "global_batch": batch * max(args.gpus, 1),
-            "parallelism": "dp%d (graph + features replicated, all-reduce of weight grads: %s)" % (
-                args.gpus, getattr(args, "dp_mode", "none")),
+            "parallelism": "dp%d (%s, all-reduce of weight grads: %s)" % (
+                args.gpus, "feature table + CSR PARTITIONED by owner = id %% world, remote rows read over NVLink peer memory "
+                "inside the gather / sampler kernels" if getattr(args, "partitioned", False) else "graph + features replicated",
+                getattr(args, "dp_mode", "none")),
             "l2_policy": "inputs larger than L2: 561 MB feature table, fresh random targets every step",
             "lr": args.lr}
 
@@ -250,6 +255,14 @@ def run_b200(args):
 
     emb = nn.Embedding(args.nodes, args.feat, device="meta")
     emb.weight = nn.Parameter(table, requires_grad=False)                  # model.py:214-215
+    if args.partitioned:
+        from graphsage import sharded
+        ex = sharded.OwnerExchange(rank, world)
+        emb = sharded.ShardedFeatures(table[rank::world, :args.feat].contiguous(), args.nodes, exchange=ex, peer=True)
+        graph = sharded.ShardedCSR.from_global(rowptr, col, rank, world, device=dev, exchange=ex, peer=True)
+        if rank != 0 or args.no_cpu_baseline:
+            del table                                                      # only the shard stays resident
+            torch.cuda.empty_cache()
     torch.manual_seed(1)
     agg1 = MeanAggregator(emb, cuda=True)
     enc1 = Encoder(emb, args.feat, args.hidden, graph, agg1, num_sample=args.k1, gcn=False, cuda=True)
@@ -415,14 +428,24 @@ def run_b200(args):
             tj = _j.load(open(tpath))           # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
             traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
             traffic_src = tj["source"]
-        roofline = {"kernel": "gather_mean_kernel (layer 1: self row + mean of k1 neighbour rows -> comb1)",
-                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "peak_source": which, "traffic": traffic, "traffic_source": traffic_src,
-                    "timing": "kernel launched alone (eager, CUDA events on its stream, 5 launches), same launch "
-                              "configuration as inside the pipelined step",
-                    "algorithmic_bytes_per_launch": g1_bytes,
-                    "rows_read": s1 + n1, "n1": n1, "s1": s1, "s2": s2, "avg_launch_ms": g1_ms,
-                    "step_share": g1_ms / sum(kernels.values())}
+        if args.partitioned and world > 1:      # the gather's rows come over NVLink: bound by the 900 GB/s/direction ingress
+            remote = (s1 + n1) * args.feat * 4 * (world - 1) / world
+            nv = remote / (g1_ms * 1e-3) / 1e9
+            roofline = {"kernel": "gather_mean_kernel<PEER> (layer 1; %d/%d of the rows read from peers over NVLink)" % (world - 1, world),
+                        "bound": "nvlink", "achieved": nv, "peak": 900.0, "unit": "GB/s", "frac": nv / 900.0,
+                        "peak_source": "NVLink 5 per-direction bandwidth per GPU (B200_PROFILING.md)", "traffic": None,
+                        "algorithmic_remote_bytes_per_launch": remote, "rows_read": s1 + n1, "n1": n1, "s1": s1, "s2": s2,
+                        "avg_launch_ms": g1_ms, "step_share": g1_ms / sum(kernels.values()),
+                        "timing": "rank 0's kernel launched alone (eager, CUDA events), peers idle"}
+        else:
+            roofline = {"kernel": "gather_mean_kernel (layer 1: self row + mean of k1 neighbour rows -> comb1)",
+                        "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "peak_source": which, "traffic": traffic, "traffic_source": traffic_src,
+                        "timing": "kernel launched alone (eager, CUDA events on its stream, 5 launches), same launch "
+                                  "configuration as inside the pipelined step",
+                        "algorithmic_bytes_per_launch": g1_bytes,
+                        "rows_read": s1 + n1, "n1": n1, "s1": s1, "s2": s2, "avg_launch_ms": g1_ms,
+                        "step_share": g1_ms / sum(kernels.values())}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -459,9 +482,9 @@ def profile_kernels(eng, B, lr, d_nodes, d_labels, iters=5):
         orig[name] = fn
 
         def timed(*a, **kw):
-            label = name
-            if name in ("gather_mean_fwd", "encoder_fwd", "encoder_bwd", "sample_csr", "encoder_fwd_tc",
-                        "encoder_wgrad_tc"):
+            label = name[:-5] if name.endswith("_peer") else name
+            if label in ("gather_mean_fwd", "encoder_fwd", "encoder_bwd", "sample_csr", "encoder_fwd_tc",
+                         "encoder_wgrad_tc"):
                 label += "[layer1]" if (kw.get("n_dev") is not None) else "[layer2]"
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -471,7 +494,7 @@ def profile_kernels(eng, B, lr, d_nodes, d_labels, iters=5):
             return out
         setattr(ops, name, timed)
 
-    for nm in ("sample_csr", "dedup_remap", "gather_mean_fwd", "encoder_fwd", "encoder_fwd_tc", "classifier_xent",
+    for nm in ("sample_csr", "sample_csr_peer", "gather_mean_fwd_peer", "dedup_remap", "gather_mean_fwd", "encoder_fwd", "encoder_fwd_tc", "classifier_xent",
                "encoder_bwd", "encoder_wgrad_tc", "encoder_dgrad", "scatter_mean_bwd", "head_rows", "head_wgrad", "sgd_step"):
         wrap(nm)
     try:

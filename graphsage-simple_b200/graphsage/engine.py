@@ -52,9 +52,13 @@ class TrainEngine:
     def __init__(self, graph1, graph2, table, feat_dim, d1, d2, num_classes, k1, k2, max_batch,
                  gcn=False, agg_gcn1=False, agg_gcn2=False, act1=ops.ACT_RELU, act2=ops.ACT_RELU,
                  uid1=1, uid2=2, device=None, use_graphs=True):
-        self.dev = torch.device(device) if device is not None else table.device
+        self.dev = torch.device(device) if device is not None else (
+            table.table.device if hasattr(table, "table_ptrs") else table.device)
         self.g1, self.g2 = graph1, graph2
-        self.table = ops.aligned_rows(table)
+        # ``table`` is the [N, F] feature matrix, or a sharded.ShardedFeatures(peer=True): the table partitioned over
+        # the ranks and read through NVLink peer memory by the gather kernel itself
+        self.table_peer = table if hasattr(table, "table_ptrs") else None
+        self.table = table.table if self.table_peer is not None else ops.aligned_rows(table)
         self.F, self.d1, self.d2, self.C = int(feat_dim), int(d1), int(d2), int(num_classes)
         self.k1, self.k2 = k1, k2
         self.gcn, self.agg_gcn1, self.agg_gcn2 = bool(gcn), bool(agg_gcn1), bool(agg_gcn2)
@@ -158,7 +162,7 @@ class TrainEngine:
         targets = fs.targets[:b]
         idx2, cnt2 = fs.idx2[:b], fs.cnt2[:b]
         # layer-2 tile over the targets (aggregators.py:42-48; RNG draw of agg2)
-        ops.sample_csr(self.g2.rowptr, self.g2.col, self.g2.num_nodes, targets, self.k2, add_self=self.agg_gcn2,
+        self._sample(self.g2, targets, self.k2, add_self=self.agg_gcn2,
                        seed=seed, step_dev=fs.step_dev, tag_head=sampling.call_tag(self.uid2, 0),
                        width=self.w2_width, idx=idx2, cnt=cnt2)
         # frontier of layer 1: [targets (SAGE self pass) | distinct hop-1 ids] (aggregators.py:52-56)
@@ -170,17 +174,29 @@ class TrainEngine:
         idx1, cnt1 = fs.idx1[:n1_max], fs.cnt1[:n1_max]
         # layer-1 tiles: rows < b are the self pass over the batch nodes (independent draw,
         # call index 1), the rest the hop-1 pass (call index 0)  -- SURVEY.md s3.2
-        ops.sample_csr(self.g1.rowptr, self.g1.col, self.g1.num_nodes, fr, self.k1, add_self=self.agg_gcn1,
+        self._sample(self.g1, fr, self.k1, add_self=self.agg_gcn1,
                        seed=seed, step_dev=fs.step_dev, tag_head=sampling.call_tag(self.uid1, 1),
                        tag_tail=sampling.call_tag(self.uid1, 0), n_head=base, n_dev=fs.n1_dev,
                        width=self.w1_width, idx=idx1, cnt=cnt1)
 
+    @staticmethod
+    def _sample(g, nodes, k, **kw):
+        """Local CSR, or a sharded.ShardedCSR(peer=True): adjacency rows of other ranks read over NVLink."""
+        if getattr(g, "rowptr_ptrs", None) is not None:
+            return ops.sample_csr_peer(g.rowptr_ptrs, g.col_ptrs, g.ex.world, g.num_nodes, nodes, k, **kw)
+        return ops.sample_csr(g.rowptr, g.col, g.num_nodes, nodes, k, **kw)
+
     def _gather(self, fs, b):
-        """Stage 2: the HBM-bound layer-1 gather-mean over the sampled tile -> comb1."""
+        """Stage 2: the HBM-bound (partitioned: NVLink-bound) layer-1 gather-mean over the sampled tile -> comb1."""
         n1_max = self._n1_max(b)
-        ops.gather_mean_fwd(self.table, self.F, fs.idx1[:n1_max], fs.cnt1[:n1_max], fs.comb1[:n1_max],
-                            neigh_off=0 if self.gcn else self.F,
-                            self_ids=None if self.gcn else fs.frontier1[:n1_max], n_dev=fs.n1_dev)
+        kw = dict(neigh_off=0 if self.gcn else self.F, self_ids=None if self.gcn else fs.frontier1[:n1_max],
+                  n_dev=fs.n1_dev)
+        if self.table_peer is not None:
+            tp = self.table_peer
+            ops.gather_mean_fwd_peer(tp.table_ptrs, tp.ex.world, tp.ld, self.F, fs.idx1[:n1_max], fs.cnt1[:n1_max],
+                                     fs.comb1[:n1_max], **kw)
+        else:
+            ops.gather_mean_fwd(self.table, self.F, fs.idx1[:n1_max], fs.cnt1[:n1_max], fs.comb1[:n1_max], **kw)
 
     def _compute_chain(self, fs, b):
         """Encoder GEMMs, classifier/loss and the whole backward for frontier set ``fs``."""
@@ -565,19 +581,21 @@ def engine_for(model, batch):
     if not (isinstance(agg1, MeanAggregator) and isinstance(agg2, MeanAggregator)):
         return None
     emb = enc1.features
-    if not (isinstance(emb, nn.Embedding) and not emb.weight.requires_grad and agg1.features is emb):
+    peer_table = getattr(emb, "table_ptrs", None) is not None            # sharded.ShardedFeatures(peer=True)
+    if not ((peer_table or (isinstance(emb, nn.Embedding) and not emb.weight.requires_grad)) and agg1.features is emb):
         return None
     if enc1.initializer in TABLE_INITIALIZERS or enc2.initializer in TABLE_INITIALIZERS:
         return None
     from .graph import CSRGraph
-    if not (isinstance(enc1.graph, CSRGraph) and isinstance(enc2.graph, CSRGraph)):
-        return None                      # partitioned graph (sharded.ShardedCSR): op-by-op path
+    fusable = lambda g: isinstance(g, CSRGraph) or getattr(g, "rowptr_ptrs", None) is not None
+    if not (fusable(enc1.graph) and fusable(enc2.graph)):
+        return None                      # partitioned graph answered by all-to-all (sharded.ShardedCSR): op-by-op path
     if not (_closure_reaches(enc2.features, enc1) and _closure_reaches(agg2.features, enc1)):
         return None
     if enc1.gcn != enc2.gcn or getattr(enc1, "base_model", None) is not None:
         return None
     act = lambda e: ops.ACT_SIGMOID if e.initializer in _SIGMOID else ops.ACT_RELU
-    eng = TrainEngine(enc1.graph, enc2.graph, emb.weight.data, enc1.feat_dim, enc1.embed_dim, enc2.embed_dim,
+    eng = TrainEngine(enc1.graph, enc2.graph, emb if peer_table else emb.weight.data, enc1.feat_dim, enc1.embed_dim, enc2.embed_dim,
                       model.weight.shape[0], enc1.num_sample, enc2.num_sample, max(batch, 1), gcn=enc1.gcn,
                       agg_gcn1=agg1.gcn, agg_gcn2=agg2.gcn, act1=act(enc1), act2=act(enc2),
                       uid1=agg1.uid, uid2=agg2.uid)

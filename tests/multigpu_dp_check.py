@@ -48,21 +48,30 @@ def main():
     batches = [np.random.default_rng(70 + s).permutation(n)[:gb] for s in range(7)]
     lr = 0.4
 
-    def fresh():
+    from graphsage import sharded
+    ex = sharded.OwnerExchange(rank, world)
+    sh_feats = sharded.ShardedFeatures(table[rank::world].contiguous(), n, exchange=ex, peer=True)
+    sh_graph = sharded.ShardedCSR.from_global(graph.rowptr_host, graph.col.cpu().numpy(), rank, world, device=dev,
+                                              exchange=ex, peer=True)
+
+    def fresh(partitioned=False):
         torch.manual_seed(5)
-        emb = torch.nn.Embedding(n, f, device="meta")
-        emb.weight = torch.nn.Parameter(table, requires_grad=False)
-        model, encs = build_sage(emb, f, [128, 128], graph, [k1, k2], c)
+        if partitioned:        # table + CSR partitioned over the ranks, read through NVLink peer memory by the fused engine
+            model, encs = build_sage(sh_feats, f, [128, 128], sh_graph, [k1, k2], c)
+        else:
+            emb = torch.nn.Embedding(n, f, device="meta")
+            emb.weight = torch.nn.Parameter(table, requires_grad=False)
+            model, encs = build_sage(emb, f, [128, 128], graph, [k1, k2], c)
         for i, e in enumerate(encs):
             e.aggregator.uid = 300 + i
         sampling.seed(13)
         return model
 
     results = {}
-    for mode in ("dp", "dp_pipelined", "single"):
-        model = fresh()
+    for mode in ("dp", "dp_pipelined", "dp_partitioned", "single"):
+        model = fresh(partitioned=(mode == "dp_partitioned"))
         eng = engine_for(model, gb)
-        assert eng is not None and eng.head
+        assert eng is not None and eng.head and (eng.table_peer is not None) == (mode == "dp_partitioned")
         if mode != "single":
             eng.peer = gdist.PeerAllreduceSGD(eng.flat_w.numel(), dev)
             eng.grad_scale = gdist.local_grad_scale(gb // world, gb, world)
@@ -71,13 +80,13 @@ def main():
             mine = nodes if mode == "single" else nodes[rank::world]
             step_lr = lr if mode == "single" else gdist.dp_lr(lr, world)
             pre = None
-            if mode == "dp_pipelined":
+            if mode in ("dp_pipelined", "dp_partitioned"):
                 pre = [(batches[j][rank::world], labels[batches[j][rank::world]]) for j in (i + 1, i + 2) if j < len(batches)] or None
             losses.append(model.train_step(mine, labels[mine], lr=step_lr, prefetch=pre))
         torch.cuda.synchronize()
         results[mode] = [p.detach().clone() for p in (model.weight, model.enc.weight, model.enc.base_model.weight)]
         dist.barrier()
-    for mode in ("dp", "dp_pipelined"):
+    for mode in ("dp", "dp_pipelined", "dp_partitioned"):
         for a, b in zip(results[mode], results["single"]):
             e = relerr(a, b)
             assert e < 1e-5, "%s weights differ from the single-rank run: %g" % (mode, e)
