@@ -185,7 +185,7 @@ __global__ void dedup_mark_kernel(const int32_t* __restrict__ idx, const int32_t
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int i = (int)(e / width), j = (int)(e - (int64_t)i * width);
-        if (j < cnt[i]) slot_of[idx[e]] = 0;       // idempotent plain store: "present"
+        if (cnt == nullptr || j < cnt[i]) slot_of[idx[e]] = 0;       // idempotent plain store: "present"
     }
 }
 
@@ -290,7 +290,7 @@ __global__ void dedup_remap_kernel(int32_t* __restrict__ idx, const int32_t* __r
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int i = (int)(e / width), j = (int)(e - (int64_t)i * width);
-        if (j < cnt[i]) idx[e] = slot_of[idx[e]];
+        if (cnt == nullptr || j < cnt[i]) idx[e] = slot_of[idx[e]];
     }
 }
 
@@ -353,7 +353,7 @@ extern "C" int32_t gs_dedup_scratch_ints(int32_t num_nodes) {
 extern "C" int gs_dedup_remap(int32_t* idx, const int32_t* cnt, int32_t n_max, const int32_t* n_dev,
                               int32_t width, int32_t num_nodes, int32_t* slot_of, int32_t* block_counts,
                               int32_t slot_base, int32_t* uniq, int32_t* n_total_dev, void* stream) {
-    if (!idx || !cnt || !slot_of || !block_counts || !uniq || !n_total_dev || num_nodes <= 0 || width <= 0 ||
+    if (!idx || !slot_of || !block_counts || !uniq || !n_total_dev || num_nodes <= 0 || width <= 0 ||
         n_max < 0)
         return GS_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;

@@ -10,10 +10,11 @@ import torch
 import torch.nn as nn
 
 from . import ops, sampling
-from .functional import GatherMean
+from .functional import GatherMean, RaggedGatherMean
 from .graph import CSRGraph
 
 TABLE_INITIALIZERS = ("1hot", "node_degree")          # aggregators.py:30, 68
+RAGGED_MIN_DEGREE = 64      # un-sampled neighbourhoods wider than this use ragged tiles instead of [n, max_degree]
 
 
 def _device():
@@ -97,6 +98,8 @@ class MeanAggregator(nn.Module):
             if not hasattr(graph, "sample"):
                 raise TypeError("MeanAggregator.forward needs to_neighs (list of sets) or graph=CSRGraph")
             ids = ops.as_ids(nodes, dev)
+            if num_sample is None and isinstance(graph, CSRGraph) and graph.max_degree > RAGGED_MIN_DEGREE:
+                return self._forward_ragged(ids, graph, initializer, dev)
             width = None
             if num_sample is None:
                 width = graph.max_degree + (1 if self.gcn else 0)
@@ -110,6 +113,17 @@ class MeanAggregator(nn.Module):
         if initializer in TABLE_INITIALIZERS:                          # aggregators.py:68-71
             embed_matrix = self.embed(self._hot_index(unique_ids, embed_matrix))
         return GatherMean.apply(embed_matrix, idx, cnt)
+
+    def _forward_ragged(self, ids, graph, initializer, dev):
+        """num_sample=None (aggregators.py:47-48) on a graph with large degrees: the whole neighbourhoods as a
+        ragged tile (offsets + flat ids) instead of a [n, max_degree] one; same dedup / lookup / mean."""
+        off, flat = ops.take_all_csr(graph.rowptr, graph.col, ids, add_self=self.gcn)
+        uniq, n_total = ops.dedup_remap(flat.view(-1, 1), None, self._dedup_scratch(graph.num_nodes, dev))
+        unique_ids = uniq[:int(n_total.item())].long()
+        embed_matrix = self.features(unique_ids)
+        if initializer in TABLE_INITIALIZERS:
+            embed_matrix = self.embed(self._hot_index(unique_ids, embed_matrix))
+        return RaggedGatherMean.apply(embed_matrix, off, flat)
 
     def _tile_plain(self, nodes, to_neighs, num_sample, dev, add_self=False):
         n = len(to_neighs)

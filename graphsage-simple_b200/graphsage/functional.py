@@ -29,6 +29,30 @@ class GatherMean(torch.autograd.Function):
         return gtable, None, None
 
 
+class RaggedGatherMean(torch.autograd.Function):
+    """The same mean for un-sampled neighbourhoods of any size (num_sample=None, aggregators.py:47-48):
+    row i averages table[flat[off[i] : off[i+1]]]."""
+
+    @staticmethod
+    def forward(ctx, table, off, flat):
+        t = ops.aligned_rows(table)
+        n, dim = off.shape[0] - 1, table.shape[1]
+        out = ops.empty_rows(n, dim, table.device)
+        ops.gather_mean_ragged(t, dim, off, flat, out)
+        ctx.save_for_backward(off, flat)
+        ctx.rows, ctx.dim = table.shape[0], dim
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        off, flat = ctx.saved_tensors
+        gtable = None
+        if ctx.needs_input_grad[0]:
+            gtable = ops.empty_rows(ctx.rows, ctx.dim, gout.device, zero=True)
+            ops.scatter_mean_ragged(ops.aligned_rows(gout), ctx.dim, off, flat, gtable)
+        return gtable, None, None
+
+
 class EncoderGemm(torch.autograd.Function):
     """h[n, d_out] = act(x . w^T): ``F.relu(self.weight.mm(combined.t()))`` of encoders.py:58-61
     in row-major form (the module returns the transposed view)."""

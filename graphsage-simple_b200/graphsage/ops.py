@@ -371,6 +371,43 @@ def sample_csr_peer(rowptr_ptrs, col_ptrs, world, num_nodes, nodes, k, add_self=
     return idx, cnt
 
 
+def take_all_csr(rowptr, col, nodes, add_self=False):
+    """Ragged full-neighbourhood tile of ``nodes`` -- see gs_take_all_count / gs_take_all_fill.
+    Returns (off int32 [n+1], flat int32 [total]); one host read of the total."""
+    lib = N.load()
+    N.require_cuda(rowptr, col, nodes)
+    n = nodes.shape[0]
+    dev = nodes.device
+    length = torch.empty(max(n, 1), device=dev, dtype=torch.int32)
+    off = torch.empty(n + 1, device=dev, dtype=torch.int32)
+    N.check(lib.gs_take_all_count(N.ptr(rowptr), N.ptr(col), N.ptr(nodes), n, int(bool(add_self)), N.ptr(length),
+                                  N.ptr(off), N.stream()), "gs_take_all_count")
+    total = int(off[n].item())
+    flat = torch.empty(max(total, 1), device=dev, dtype=torch.int32)[:total]
+    N.check(lib.gs_take_all_fill(N.ptr(rowptr), N.ptr(col), N.ptr(nodes), n, N.ptr(off), N.ptr(flat), N.stream()),
+            "gs_take_all_fill")
+    LAUNCHES[0] += 3
+    return off, flat
+
+
+def gather_mean_ragged(table, dim, off, flat, out):
+    lib = N.load()
+    N.require_cuda(table, off, flat, out)
+    N.check(lib.gs_gather_mean_ragged(N.ptr(table), table.stride(0), int(dim), N.ptr(off), N.ptr(flat), off.shape[0] - 1,
+                                      N.ptr(out), out.stride(0), N.stream()), "gs_gather_mean_ragged")
+    LAUNCHES[0] += 1
+    return out
+
+
+def scatter_mean_ragged(gout, dim, off, flat, gtable):
+    lib = N.load()
+    N.require_cuda(gout, off, flat, gtable)
+    N.check(lib.gs_scatter_mean_ragged(N.ptr(gout), gout.stride(0), int(dim), N.ptr(off), N.ptr(flat), off.shape[0] - 1,
+                                       N.ptr(gtable), gtable.stride(0), N.stream()), "gs_scatter_mean_ragged")
+    LAUNCHES[0] += 1
+    return gtable
+
+
 def advance_step(step_dev):
     N.check(N.load().gs_advance_step(N.ptr(step_dev), N.stream()), "gs_advance_step")
     LAUNCHES[0] += 1

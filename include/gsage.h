@@ -72,7 +72,8 @@ GS_API int gs_sample_csr(const int64_t* rowptr, const int32_t* col, int32_t num_
  * Replaces `unique_nodes_list = list(set.union(*samp_neighs))` and the id->column dict,
  * aggregators.py:52-56.  Distinct ids of the tile, ascending, are written to uniq[0..U);
  * the tile is rewritten in place as positions slot_base + rank; *n_total_dev = slot_base + U.
- * slot_of[num_nodes] and block_counts[gs_dedup_scratch_ints(num_nodes)] are scratch.     */
+ * slot_of[num_nodes] and block_counts[gs_dedup_scratch_ints(num_nodes)] are scratch.
+ * cnt == NULL: every entry of idx is valid (flat ragged index array: n_max = entries, width = 1). */
 GS_API int32_t gs_dedup_scratch_ints(int32_t num_nodes);
 GS_API int gs_dedup_remap(int32_t* idx, const int32_t* cnt, int32_t n_max, const int32_t* n_dev,
                    int32_t width, int32_t num_nodes, int32_t* slot_of, int32_t* block_counts,
@@ -99,6 +100,24 @@ GS_API int gs_scatter_mean_bwd(const float* gout, int64_t ld_gout, int32_t neigh
                         const int32_t* idx, const int32_t* cnt, int32_t width,
                         const int32_t* self_ids, int32_t n_max, const int32_t* n_dev,
                         float* gtable, int64_t ld_gtable, void* stream);
+
+/* ---- full neighbourhood (num_sample=None) over ragged tiles ----------------------------------------
+ * Replaces the un-sampled path of MeanAggregator.forward (aggregators.py:47-48 with the lookup of
+ * encoders.py:47 and the self-loop union of aggregators.py:50-51) and its mean / backward
+ * (aggregators.py:54-74, model.py:249) without a tile as wide as the largest degree:
+ *   gs_take_all_count: len[i] = deg(nodes[i]) (+1 if add_self and the node is not its own neighbour),
+ *                      off[0..n] = exclusive prefix sums (off[n] = total entries)
+ *   gs_take_all_fill:  flat[off[i] .. off[i+1]) = the row (ascending) [+ the node itself]
+ *   gs_gather_mean_ragged:  out[i, :] = mean_e table[flat[e], :]        (zeros for empty rows)
+ *   gs_scatter_mean_ragged: gtable[flat[e], :] += gout[i, :] / len(i)   (caller-zeroed gtable)        */
+GS_API int gs_take_all_count(const int64_t* rowptr, const int32_t* col, const int32_t* nodes, int32_t n,
+                      int32_t add_self, int32_t* len, int32_t* off, void* stream);
+GS_API int gs_take_all_fill(const int64_t* rowptr, const int32_t* col, const int32_t* nodes, int32_t n,
+                     const int32_t* off, int32_t* flat, void* stream);
+GS_API int gs_gather_mean_ragged(const float* table, int64_t ld_table, int32_t dim, const int32_t* off,
+                          const int32_t* flat, int32_t n, float* out, int64_t ld_out, void* stream);
+GS_API int gs_scatter_mean_ragged(const float* gout, int64_t ld_gout, int32_t dim, const int32_t* off,
+                           const int32_t* flat, int32_t n, float* gtable, int64_t ld_gtable, void* stream);
 
 /* ---- K3: encoder GEMM + activation --------------------------------------------------------
  * Replaces `F.relu(self.weight.mm(combined.t()))` / sigmoid, encoders.py:58-61.

@@ -426,3 +426,47 @@ def test_degenerate_batches(ops):
     empty_ids = torch.zeros(0, dtype=torch.int32, device="cuda")
     i0, c0 = ops.sample_csr(dev(np.array([0, 1], dtype=np.int64)), dev(np.array([0], dtype=np.int32)), 1, empty_ids, 5)
     assert i0.shape == (0, 5) and c0.shape == (0,)
+
+
+@pytest.mark.parametrize("add_self", [False, True])
+def test_ragged_full_neighbourhood(ops, add_self):
+    """num_sample=None over ragged tiles (gs_take_all_*, gs_gather_mean_ragged, gs_scatter_mean_ragged): bit-exact
+    index work against the CSR, mean / backward against fp64, on a graph with a 5000-neighbour hub, isolated nodes
+    and self loops."""
+    rng = np.random.default_rng(21)
+    n, dim = 6000, 37
+    rowptr, col = random_csr(rng, n, 8, hub=5000)
+    nodes = np.concatenate([rng.integers(0, n, 700), np.argsort(-np.diff(rowptr))[:3]]).astype(np.int32)
+    off, flat = ops.take_all_csr(dev(rowptr), dev(col), dev(nodes), add_self=add_self)
+    off_h, flat_h = off.cpu().numpy(), flat.cpu().numpy()
+    want = []
+    for v in nodes:
+        row = col[rowptr[v]:rowptr[v + 1]].tolist()
+        if add_self and v not in row:
+            row = row + [int(v)]
+        want.append(row)
+    assert np.array_equal(np.diff(off_h), [len(r) for r in want]) and off_h[0] == 0
+    assert np.array_equal(flat_h, np.concatenate([np.array(r, dtype=np.int32) for r in want]))
+    assert max(len(r) for r in want) >= 5000
+    table = rng.standard_normal((n, dim)).astype(np.float32)
+    t = ops.empty_rows(n, dim, "cuda"); t.copy_(dev(table))
+    out = ops.empty_rows(len(nodes), dim, "cuda", zero=True)
+    ops.gather_mean_ragged(t, dim, off, flat, out)
+    ref = np.stack([table[r].astype(np.float64).mean(0) if r else np.zeros(dim) for r in want])
+    assert relerr(out.cpu().numpy(), ref) < REL
+    gout = rng.standard_normal((len(nodes), dim)).astype(np.float32)
+    g = ops.empty_rows(len(nodes), dim, "cuda"); g.copy_(dev(gout))
+    gt = ops.empty_rows(n, dim, "cuda", zero=True)
+    ops.scatter_mean_ragged(g, dim, off, flat, gt)
+    gref = np.zeros((n, dim))
+    for i, r in enumerate(want):
+        if r:
+            np.add.at(gref, r, gout[i].astype(np.float64) / len(r))
+    assert relerr(gt.cpu().numpy(), gref) < REL
+    # flat dedup (cnt = NULL): distinct ids ascending, flat rewritten to their ranks
+    scratch = ops.DedupScratch(n, "cuda")
+    f2 = flat.clone()
+    uniq, tot = ops.dedup_remap(f2.view(-1, 1), None, scratch)
+    u = np.unique(flat_h)
+    assert int(tot.item()) == u.size and np.array_equal(uniq[:u.size].cpu().numpy(), u)
+    assert np.array_equal(u[f2.cpu().numpy()], flat_h)

@@ -340,3 +340,34 @@ def test_fused_engine_wide_layers_equal_op_by_op_path(gcn, feat, batch):
         assert abs(a[0] - b[0]) <= REL * max(abs(a[0]), 1e-30)
         for x, y in zip(a[1:], b[1:]):
             assert relerr(y.cpu().numpy(), x.cpu().numpy()) < REL
+
+
+@pytest.mark.parametrize("gcn", [False, True])
+def test_full_neighbourhood_forward_on_hub_graph_matches_oracle(gcn):
+    """model.forward(val) with num_sample=None (the un-sampled validation forward, model.py:256 /
+    aggregators.py:47-48) on a graph whose largest degree (700) forces the ragged-tile path: scores equal the
+    oracle's dense-mask formulation on the same adjacency."""
+    from oracle import ref_path as R
+    rng = np.random.default_rng(9)
+    n, f, c = 900, 20, 5
+    adj = {v: set() for v in range(n)}
+    src, dst = rng.integers(0, n, (2, 3 * n))
+    hub = np.arange(700)
+    for a, b in zip(np.concatenate([src, np.full(700, 899), np.arange(n)]),
+                    np.concatenate([dst, hub, (np.arange(n) + 1) % n])):
+        if a != b:
+            adj[int(a)].add(int(b)); adj[int(b)].add(int(a))
+    g = {"table": rng.standard_normal((n, f)).astype(np.float32),
+         "w1": (rng.standard_normal((16, f if gcn else 2 * f)) / 5).astype(np.float32),
+         "w2": (rng.standard_normal((12, 16 if gcn else 32)) / 4).astype(np.float32),
+         "wc": (rng.standard_normal((c, 12)) / 3).astype(np.float32)}
+    model, enc1, enc2 = build_model(g, gcn, adj, adj, None, None)
+    assert enc1.graph.max_degree >= 700
+    nodes = np.concatenate([[899], rng.permutation(n)[:40]])
+    scores = model.forward(list(nodes))
+    oracle = R.TwoLayerModel(torch.from_numpy(g["table"]), adj, adj, 16, 12, c, None, None, gcn=gcn,
+                             w1=torch.from_numpy(g["w1"]), w2=torch.from_numpy(g["w2"]), wc=torch.from_numpy(g["wc"]))
+    ref = oracle.forward(list(nodes))
+    assert relerr(scores.detach().cpu().numpy(), ref.detach().numpy()) < REL
+    scores.sum().backward()                         # the ragged backward runs and produces finite weight gradients
+    assert torch.isfinite(enc1.weight.grad).all() and enc1.weight.grad.abs().max() > 0
