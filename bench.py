@@ -350,7 +350,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = world * B * K / (ms_total / 1e3)
-    done = eng.sets[(eng.cur - 1) % eng.depth]           # the set whose compute chain ran last
+    done = eng.sets[(eng.cur - 1) % eng.slots]           # the set whose compute chain ran last
     n1 = int(done.n1_dev.item())
     s1 = int(done.cnt1[:n1].sum().item())
     s2 = int(done.cnt2[:B].sum().item())

@@ -125,7 +125,7 @@ class TrainEngine:
         self._graphs = {}
         self._warm = set()
         self._launch_count = {}
-        self._side = self._gstream = self._sstream = None
+        self._side = self._gstream = self._sstream = self._cstream = None
         self._loss_ring = None
         self._pending_lr = None
         self.queue = []            # batches in flight: {slot, b, state (0 staged, 1 sampled, 2 gathered), ids}
@@ -282,11 +282,11 @@ class TrainEngine:
         if b1 is not None:
             self._gstream.wait_stream(main)
             with torch.cuda.stream(self._gstream):
-                self._gather(self.sets[(p + 1) % self.depth], b1)
+                self._gather(self.sets[(p + 1) % self.slots], b1)
         if b2 is not None:
             self._sstream.wait_stream(main)
             with torch.cuda.stream(self._sstream):
-                self._sample_chain(self.sets[(p + 2) % self.depth], b2)
+                self._sample_chain(self.sets[(p + 2) % self.slots], b2)
         if lead_lr is not None:
             self._update(lead_lr)
         self._compute_chain(self.sets[p], b0)
@@ -403,10 +403,16 @@ class TrainEngine:
     #   C  GEMMs / loss / backward / SGD of batch t  (tensor pipe + L2)
     # so the HBM pipe never idles behind the sampler and the tensor pipe never behind the gather.
     depth = 3
+    # One frontier set more than stages: the set that batch t+3 is staged into is then not in use by any stage of
+    # step t, so its 12 KB staging copy runs on a copy stream DURING step t instead of between two graphs.
+    slots = 4
 
     def enable_pipeline(self):
-        while len(self.sets) < self.depth:
+        while len(self.sets) < self.slots:
             self.sets.append(_FrontierSet(self))
+        if self._cstream is None:
+            self._cstream = torch.cuda.Stream(device=self.dev, priority=-1)
+            self._slot_done = [None] * self.slots
         if self._gstream is None:
             # the side streams outrank the main stream: their short kernels must not queue behind the
             # second wave of a 200+-CTA GEMM grid (measured: a 35 us stall per step, profiles/README.md)
@@ -423,8 +429,19 @@ class TrainEngine:
 
     def reset_pipeline(self):
         self.flush_update()
+        if self._cstream is not None:                 # staging copies of dropped batches must not outlive the reset
+            torch.cuda.current_stream().wait_stream(self._cstream)
+            self._slot_done = [None] * self.slots     # next pushes order themselves after everything enqueued so far
         self.queue = []
         self.cur = 0
+
+    def drop_queued(self, keep):
+        """Forget the queued batches after the first ``keep`` (a different batch was announced than the one
+        that was prefetched); their sets may have been sampled / gathered by the last step, so the next
+        staging copy into them waits for all work enqueued so far instead of the per-set event."""
+        for e in self.queue[keep:]:
+            self._slot_done[e["slot"]] = None
+        del self.queue[keep:]
 
     def push(self, nodes, labels, step, on_device=False, packed=None):
         """Stage the next minibatch (host ids/labels, device tensors with ``on_device``, or a block made
@@ -433,12 +450,21 @@ class TrainEngine:
         self.enable_pipeline()
         if len(self.queue) >= self.depth:
             raise RuntimeError("pipeline queue is full (%d batches in flight)" % self.depth)
-        slot = (self.cur + len(self.queue)) % self.depth
-        if packed is not None:
-            b = self.stage_packed(packed[0], packed[1], slot=slot)
+        slot = (self.cur + len(self.queue)) % self.slots
+        # the copy runs on the copy stream, after the last graph that used this set (as its compute set) has finished
+        main = torch.cuda.current_stream()
+        if self._slot_done[slot] is not None:
+            self._cstream.wait_event(self._slot_done[slot])
         else:
-            b = (self.stage_device if on_device else self.stage)(nodes, labels, step, slot=slot)
-        self.queue.append({"slot": slot, "b": b, "state": 0,
+            self._cstream.wait_stream(main)
+        with torch.cuda.stream(self._cstream):
+            if packed is not None:
+                b = self.stage_packed(packed[0], packed[1], slot=slot)
+            else:
+                b = (self.stage_device if on_device else self.stage)(nodes, labels, step, slot=slot)
+            staged = torch.cuda.Event()
+            staged.record()
+        self.queue.append({"slot": slot, "b": b, "state": 0, "staged": staged,
                            "ids": None if (on_device or packed is not None) else np.array(nodes, dtype=np.int64, copy=True)})
         return b
 
@@ -450,6 +476,11 @@ class TrainEngine:
             raise RuntimeError("step_pipelined: no batch queued (call push first)")
         p = self.cur
         assert q[0]["slot"] == p
+        main_stream = torch.cuda.current_stream()
+        for e in q:                                   # inputs staged on the copy stream are visible to this step
+            if e["staged"] is not None:
+                main_stream.wait_event(e["staged"])
+                e["staged"] = None
         if q[0]["state"] < 1:
             self._run(("s", q[0]["b"], p), lambda: self._sample_chain(self.sets[p], q[0]["b"]))
             q[0]["state"] = 1
@@ -483,12 +514,12 @@ class TrainEngine:
             if b1 is not None:
                 self._gstream.wait_stream(main)
                 with torch.cuda.stream(self._gstream):
-                    self._run(("g", b1, (p + 1) % self.depth), lambda: self._gather(self.sets[(p + 1) % self.depth], b1))
+                    self._run(("g", b1, (p + 1) % self.slots), lambda: self._gather(self.sets[(p + 1) % self.slots], b1))
             if b2 is not None:
                 self._sstream.wait_stream(main)
                 with torch.cuda.stream(self._sstream):
-                    self._run(("s", b2, (p + 2) % self.depth),
-                              lambda: self._sample_chain(self.sets[(p + 2) % self.depth], b2))
+                    self._run(("s", b2, (p + 2) % self.slots),
+                              lambda: self._sample_chain(self.sets[(p + 2) % self.slots], b2))
             self._run(("cchain", b0, p), lambda: self._compute_chain(self.sets[p], b0))
             allreduce(self.flat_g)
             self.update(lr)
@@ -501,7 +532,10 @@ class TrainEngine:
         if b2 is not None:
             q[2]["state"] = 1
         q.pop(0)
-        self.cur = (p + 1) % self.depth
+        done = torch.cuda.Event()
+        done.record()                                 # set p may be restaged once this step has finished
+        self._slot_done[p] = done
+        self.cur = (p + 1) % self.slots
 
     def read_loss(self):
         self.loss_host.copy_(self.loss, non_blocking=True)

@@ -116,10 +116,11 @@ class SupervisedGraphSage(nn.Module):
                 eng.push(nodes, labels, step)
             for j, (nn, ll) in enumerate(upcoming[:eng.depth - 1]):
                 if len(eng.queue) > j + 1 and not same(eng.queue[j + 1], nn):
-                    del eng.queue[j + 1:]                    # a different batch was announced earlier
+                    eng.drop_queued(j + 1)                   # a different batch was announced earlier
                 if len(eng.queue) <= j + 1:
                     eng.push(nn, ll, step + 1 + j)
-            del eng.queue[len(upcoming) + 1:]
+            if len(eng.queue) > len(upcoming) + 1:
+                eng.drop_queued(len(upcoming) + 1)
             eng.step_pipelined(lr, self.grad_allreduce)
         return eng.read_loss() if sync else eng.read_loss_async()
 
