@@ -22,7 +22,12 @@ import time
 
 import numpy as np
 
-os.environ["NCCL_DEBUG"] = os.environ.get("GSAGE_NCCL_DEBUG", "WARN")   # keep NCCL banners off stdout (ONE JSON line)
+# ONE JSON line on stdout: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION and above (WARN included),
+# so the variable is removed unless a debug level is asked for explicitly
+if os.environ.get("GSAGE_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = os.environ["GSAGE_NCCL_DEBUG"]
+else:
+    os.environ.pop("NCCL_DEBUG", None)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "graphsage-simple_b200")):
     if p not in sys.path:

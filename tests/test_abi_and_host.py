@@ -67,3 +67,35 @@ def test_modules_refuse_to_run_without_cuda():
     from graphsage.aggregators import MeanAggregator
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         MeanAggregator(nn.Embedding(4, 4))
+
+
+def test_bench_graph_generators_are_consistent():
+    """Host logic of bench.py: the per-rank partitioned graph builder (config 5) must produce exactly the rows
+    v % world == rank of the single-rank build, symmetric, deduplicated, sorted; the R-MAT variant is symmetric,
+    heavy-tailed and leaves no node without an edge."""
+    import bench
+    n, pairs = 3001, 20000
+    rp1, col1 = bench.build_partitioned_graph(n, pairs, 0, 1, seed=5, chunk=4096)
+    deg = np.diff(rp1)
+    edges = set(zip(np.repeat(np.arange(n), deg).tolist(), col1.tolist()))
+    assert all((b, a) in edges for a, b in edges) and len(edges) == col1.size
+    assert all(np.all(np.diff(col1[rp1[v]:rp1[v + 1]]) > 0) for v in range(n))
+    world = 3
+    total = 0
+    for rank in range(world):
+        rp, col = bench.build_partitioned_graph(n, pairs, rank, world, seed=5, chunk=4096)
+        assert rp.shape == (n + 1,)
+        for v in range(n):
+            row = col[rp[v]:rp[v + 1]]
+            if v % world == rank:
+                assert np.array_equal(row, col1[rp1[v]:rp1[v + 1]])
+            else:
+                assert row.size == 0
+        total += col.size
+    assert total == col1.size
+    rp, col = bench.build_graph_arrays(4000, 40000, "rmat")
+    d = np.diff(rp)
+    e = set(zip(np.repeat(np.arange(4000), d).tolist(), col.tolist()))
+    assert d.min() >= 1 and d.max() > 20 * d.mean() and all((b, a) in e for a, b in e)
+    rp_u, col_u = bench.build_graph_arrays(4000, 40000)
+    assert np.diff(rp_u).max() < 5 * np.diff(rp_u).mean()
