@@ -99,3 +99,34 @@ def test_bench_graph_generators_are_consistent():
     assert d.min() >= 1 and d.max() > 20 * d.mean() and all((b, a) in e for a, b in e)
     rp_u, col_u = bench.build_graph_arrays(4000, 40000)
     assert np.diff(rp_u).max() < 5 * np.diff(rp_u).mean()
+
+
+def test_every_exported_symbol_is_documented():
+    """INTEGRATION.md names every entry point of include/gsage.h next to the reference lines it replaces."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in header_symbols() if n not in doc]
+    assert not missing, missing
+
+
+def test_host_helpers():
+    """Pure host logic of the drop-in package (no CUDA): sampler tags, data-parallel scaling, CSR builders."""
+    from graphsage import dist as gd, sampling
+    from graphsage.graph import CSRGraph
+    sampling.seed(7)
+    assert sampling.get_seed() == 7 and sampling.get_step() == 0
+    with sampling.top_level_call() as s1:
+        with sampling.top_level_call() as inner:            # nested encoder call: same minibatch, same step
+            assert inner == s1 == 1
+    with sampling.top_level_call() as s2:
+        assert s2 == 2
+    assert sampling.call_tag(3, 1) != sampling.call_tag(3, 0) != sampling.call_tag(4, 0)
+    nodes, labels = np.arange(10), np.arange(10)
+    parts = [gd.shard_batch(nodes, labels, r, 3)[0] for r in range(3)]
+    assert np.array_equal(np.concatenate(parts), nodes) and max(map(len, parts)) - min(map(len, parts)) <= 1
+    assert abs(sum(gd.local_grad_scale(len(p), 10, 3) for p in parts) / 3 - 1.0) < 1e-12
+    assert gd.dp_lr(0.7, 8) == 0.7 / 8
+    g = CSRGraph.from_edges([0, 0, 2, 2], [1, 1, 0, 2], 4, device="cpu")       # duplicate edge, self loop, isolated node 3
+    assert g.rowptr_host.tolist() == [0, 2, 3, 5, 5] and g.col.tolist() == [1, 2, 0, 0, 2]
+    assert g.max_degree == 2 and g.min_degree == 0 and g.to_adj_lists() == {0: {1, 2}, 1: {0}, 2: {0, 2}, 3: set()}
+    h = CSRGraph.from_adj_lists({0: {2, 1}, 2: {0}}, num_nodes=4, device="cpu")
+    assert h.rowptr_host.tolist() == [0, 2, 2, 3, 3] and h.col.tolist() == [1, 2, 0]
