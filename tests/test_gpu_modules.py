@@ -371,3 +371,43 @@ def test_full_neighbourhood_forward_on_hub_graph_matches_oracle(gcn):
     assert relerr(scores.detach().cpu().numpy(), ref.detach().numpy()) < REL
     scores.sum().backward()                         # the ragged backward runs and produces finite weight gradients
     assert torch.isfinite(enc1.weight.grad).all() and enc1.weight.grad.abs().max() > 0
+
+
+def test_three_layer_train_step_matches_reference(golden):
+    """The depth of BASELINE config 5: three Encoders stacked by closure recursion (model.py:218-227 extended by one
+    layer), replaying the reference's sampled neighbour lists; scores, loss, all four gradients and the SGD update
+    against golden outputs of the UNMODIFIED reference (tests/golden/make_golden_3layer.py)."""
+    from graphsage.aggregators import MeanAggregator
+    from graphsage.encoders import Encoder
+    from graphsage.model import SupervisedGraphSage
+    g = golden("model_3layer")
+    n, f = g["table"].shape
+    S = [tiles_to_adj(np.arange(n), g["idx%d" % l], g["cnt%d" % l]) for l in (1, 2, 3)]
+    emb = embedding_of(g["table"])
+    agg1 = MeanAggregator(emb, cuda=True)
+    enc1 = Encoder(emb, f, g["w1"].shape[0], S[0], agg1, num_sample=None, gcn=False, cuda=True)
+    agg2 = MeanAggregator(lambda nodes: enc1(nodes).t(), cuda=True)
+    enc2 = Encoder(lambda nodes: enc1(nodes).t(), enc1.embed_dim, g["w2"].shape[0], S[1], agg2, num_sample=None,
+                   base_model=enc1, gcn=False, cuda=True)
+    agg3 = MeanAggregator(lambda nodes: enc2(nodes).t(), cuda=True)
+    enc3 = Encoder(lambda nodes: enc2(nodes).t(), enc2.embed_dim, g["w3"].shape[0], S[2], agg3, num_sample=None,
+                   base_model=enc2, gcn=False, cuda=True)
+    model = SupervisedGraphSage(g["wc"].shape[0], enc3)
+    with torch.no_grad():
+        for p, key in ((enc1.weight, "w1"), (enc2.weight, "w2"), (enc3.weight, "w3"), (model.weight, "wc")):
+            p.copy_(torch.from_numpy(g[key]))
+    assert sorted(k for k, q in model.named_parameters() if q.requires_grad) == sorted(
+        ["weight", "enc.weight", "enc.base_model.weight", "enc.base_model.base_model.weight"])
+    nodes = list(g["nodes"])
+    scores = model.forward(nodes)
+    assert relerr(scores.detach().cpu().numpy(), g["scores"]) < REL
+    opt = torch.optim.SGD(filter(lambda p: p.requires_grad, model.parameters()), lr=0.7)
+    opt.zero_grad()
+    loss = model.loss(nodes, torch.LongTensor(g["labels"][g["nodes"]]))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])) < REL
+    for p, key in ((model.weight, "gwc"), (enc3.weight, "gw3"), (enc2.weight, "gw2"), (enc1.weight, "gw1")):
+        assert relerr(p.grad.cpu().numpy(), g[key]) < REL, key
+    opt.step()
+    for p, key in ((model.weight, "wc_new"), (enc3.weight, "w3_new"), (enc1.weight, "w1_new")):
+        assert relerr(p.detach().cpu().numpy(), g[key]) < REL, key
