@@ -12,6 +12,7 @@ Contents
   ref_path.py      torch-CPU restatement of the reference's algorithm
                    (graphsage/aggregators.py:34-76, graphsage/encoders.py:40-62,
                    graphsage/model.py:52-69, 237-250 of zjzijielu/graphsage-simple).
+                   (Layer, TwoLayerModel, StackedModel for any depth).
                    PINNED: checked against outputs of the unmodified reference imported
                    from /root/reference (tests/golden/*.npz, made by
                    tests/golden/make_golden.py) -- see tests/test_oracle_golden.py.

@@ -169,6 +169,36 @@ class TwoLayerModel:
         return loss.detach()
 
 
+class StackedModel:
+    """The same wiring for ANY depth (BASELINE config 5 is three layers deep): layer l's lookup is the closure
+    ``lambda ids: layer_{l-1}(ids).t()`` (model.py:220-221 applied repeatedly), the classifier sits on the last
+    layer (model.py:52-69).  ``adjs``, ``dims`` and ``ks`` are per layer, innermost first."""
+
+    def __init__(self, table, adjs, dims, num_classes, ks, gcn=False, weights=None, wc=None, rng=_random):
+        self.table = table
+        self.layers = []
+        lookup, feat_dim = (lambda ids: table[ids]), table.shape[1]
+        for l, (adj, dim, k) in enumerate(zip(adjs, dims, ks)):
+            layer = Layer(lookup, feat_dim, dim, adj, k, gcn, False, "None", None,
+                          None if weights is None else weights[l], rng)
+            self.layers.append(layer)
+            lookup, feat_dim = (lambda ids, below=layer: below(ids).t()), dim
+        if wc is None:
+            wc = torch.empty(num_classes, dims[-1])
+            torch.nn.init.xavier_uniform_(wc)
+        self.weight = wc.clone().requires_grad_(True)
+
+    def parameters(self):
+        return [self.weight] + [p for layer in reversed(self.layers) for p in layer.parameters()]
+
+    def forward(self, nodes):
+        return self.weight.mm(self.layers[-1](nodes)).t()
+
+    def loss(self, nodes, labels):
+        labels = torch.as_tensor(np.asarray(labels), dtype=torch.long).reshape(-1)
+        return torch.nn.functional.cross_entropy(self.forward(nodes), labels)
+
+
 def adj_from_csr(rowptr, col):
     """CSR -> the reference's ``adj_lists`` mapping (model.py:303-310 builds the same
     structure from the edge file)."""
