@@ -130,3 +130,25 @@ def test_host_helpers():
     assert g.max_degree == 2 and g.min_degree == 0 and g.to_adj_lists() == {0: {1, 2}, 1: {0}, 2: {0, 2}, 3: set()}
     h = CSRGraph.from_adj_lists({0: {2, 1}, 2: {0}}, num_nodes=4, device="cpu")
     assert h.rowptr_host.tolist() == [0, 2, 2, 3, 3] and h.col.tolist() == [1, 2, 0]
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm: oracle port of the reference's dense-mask path on the host cores)
+    prints exactly one JSON line with the contract's keys, also when launched as rank 1 of a torchrun (no output)."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--nodes", "4000", "--pairs", "40000", "--feat", "20", "--hidden", "16", "--classes", "5", "--cpu-batch", "32"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in j, key
+    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
+    assert j["cpu_baseline"]["cores"] >= 1 and j["e2e"]["h2d_bytes_per_step"] == 0 and j["vs_baseline"] is None
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
