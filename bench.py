@@ -22,12 +22,12 @@ import time
 
 import numpy as np
 
-# ONE JSON line on stdout: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION and above (WARN included),
-# so the variable is removed unless a debug level is asked for explicitly
+# ONE JSON line on stdout: NCCL writes its banner / INFO lines to stdout by default, so whatever NCCL_DEBUG level the
+# caller asked for is kept but routed to stderr (or to the NCCL_DEBUG_FILE the caller named)
 if os.environ.get("GSAGE_NCCL_DEBUG"):
     os.environ["NCCL_DEBUG"] = os.environ["GSAGE_NCCL_DEBUG"]
-else:
-    os.environ.pop("NCCL_DEBUG", None)
+if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "graphsage-simple_b200")):
     if p not in sys.path:
@@ -121,30 +121,48 @@ class LazyAdj(dict):
 
 
 def cpu_reference_rate(args, rowptr, col, table, labels, w1, w2, wc, batch, steps, warmup=1):
-    """Time the oracle port of the reference's CPU path (dense-mask formulation, Python
-    sampling) on this box's host cores.  Returns (targets/s, cores, description)."""
+    """Time the reference's CPU path on this box's host cores: the UNMODIFIED reference modules from oracle/_ref
+    (oracle/build_ref.py; kind "reference") driven through its own loop (model.py:245-250), or, when oracle/_ref did
+    not travel, the oracle port of the same formulation (kind "port").  Returns (targets/s, cores, kind, description)."""
+    import contextlib
     import random
     import torch
     from oracle import ref_path as R
+    from oracle import ref_runtime as RR
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     adj = LazyAdj(rowptr, col)
-    model = R.TwoLayerModel(table, adj, adj, args.hidden, args.hidden, args.classes, args.k1, args.k2,
-                            gcn=False, w1=w1, w2=w2, wc=wc)
+    kind = "port"
+    if RR.available() and not os.environ.get("GSAGE_REFERENCE_PORT"):
+        try:
+            with contextlib.redirect_stdout(sys.stderr):          # the reference's Encoder prints its dimensions
+                ref = RR.build_two_layer(table, adj, args.feat, args.hidden, args.hidden, args.classes, args.k1, args.k2,
+                                         gcn=False, weights=(w1, w2, wc))
+                opt = RR.make_optimizer(ref, args.lr)
+            step = lambda nodes: RR.train_step(ref, opt, list(nodes), labels[nodes])
+            kind = "reference"
+        except Exception as e:                                    # e.g. a dependency of the reference's model.py is absent
+            print("oracle/_ref not usable (%s); timing the oracle port" % str(e).splitlines()[0], file=sys.stderr)
+    if kind == "port":
+        model = R.TwoLayerModel(table, adj, adj, args.hidden, args.hidden, args.classes, args.k1, args.k2,
+                                gcn=False, w1=w1, w2=w2, wc=wc)
+        step = lambda nodes: model.train_step(list(nodes), labels[nodes], lr=args.lr)
     random.seed(1)
     rng = np.random.default_rng(7)
     times = []
     for it in range(warmup + steps):
         nodes = rng.integers(0, args.nodes, batch)
         t0 = time.perf_counter()
-        model.train_step(list(nodes), labels[nodes], lr=args.lr)
+        step(nodes)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     med = float(np.median(times))
-    return batch / med, cores, ("bounded sample of the workload: B=%d targets/step (the dense B x U mask of the "
-                                "reference's formulation is 4.75 GB at 512), %d warm-up + %d timed steps, median "
-                                "%.3f s/step, %d torch threads" % (batch, warmup, steps, med, cores))
+    what = ("the unmodified reference modules (oracle/_ref: graphsage.aggregators / encoders / model.SupervisedGraphSage, "
+            "loop of model.py:245-250)" if kind == "reference" else "oracle port of the reference's dense-mask formulation")
+    return batch / med, cores, kind, ("%s; bounded sample of the workload: B=%d targets/step (the dense B x U mask of the "
+                                      "reference's formulation is 4.75 GB at 512), %d warm-up + %d timed steps, median "
+                                      "%.3f s/step, %d torch threads" % (what, batch, warmup, steps, med, cores))
 
 
 class ClockSampler(threading.Thread):
@@ -204,13 +222,20 @@ def run_reference(args):
         torch.nn.init.xavier_uniform_(w)
         ws.append(w)
     t0 = time.perf_counter()
-    rate, cores, sample = cpu_reference_rate(args, rowptr, col, table, labels, *ws, batch=args.cpu_batch,
-                                             steps=max(args.steps, 1), warmup=max(args.warmup, 1))
+    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
+    rate, cores, kind, sample = cpu_reference_rate(args, rowptr, col, table, labels, *ws, batch=args.cpu_batch,
+                                                   steps=steps, warmup=warmup)
+    # the config states what THIS arm ran: the reference's dense mask does not fit beyond B = 512, so its batch is
+    # --cpu-batch (256), not the 1024 of the B200 arm; one process on the host cores whatever --gpus says
+    cfg = workload_config(args, args.cpu_batch)
+    cfg["global_batch"] = args.cpu_batch
+    cfg["parallelism"] = "one CPU process, %d torch threads (rank 0 only; --gpus %d ignored)" % (cores, args.gpus)
+    cfg["b200_arm_batch_per_gpu"] = args.batch
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.cpu_batch / rate,
+            "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * args.cpu_batch / rate,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args, args.batch),
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
     print(json.dumps(line))
@@ -464,9 +489,9 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        rate, cores, sample = cpu_reference_rate(args, rowptr, col, table[:, :args.feat].cpu().contiguous(), labels_np,
-                                                 *w0, batch=args.cpu_batch, steps=args.cpu_steps)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        rate, cores, kind, sample = cpu_reference_rate(args, rowptr, col, table[:, :args.feat].cpu().contiguous(), labels_np,
+                                                       *w0, batch=args.cpu_batch, steps=args.cpu_steps)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

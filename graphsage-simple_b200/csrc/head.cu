@@ -400,12 +400,16 @@ extern "C" int gs_head_supported(int32_t d1, int32_t k2_in, int32_t d2, int32_t 
     return head_smem_bytes(k2_in, num_classes) <= 227 * 1024 ? 1 : 0;
 }
 
-// ws layout (floats): dz2[n*128] | dl[n*C] | loss_rows[n] | part[tiles*kSplits*2048] | tickets[tiles] (int32, zeroed once by the caller)
+// ws layout (floats): tickets[tiles] (int32, zeroed once by the caller, re-armed by every launch) | part[tiles*kSplits*2048] |
+// dz2[n*128] | dl[n*C] | loss_rows[n].  The tickets and the partial tiles come FIRST, at offsets that depend only on
+// (K2, C): a workspace sized for a capacity n_max serves every call with n <= n_max, and the tickets a launch with
+// n = n_max re-armed are the ones a later launch with a smaller n reads.
 extern "C" int64_t gs_head_ws_floats(int32_t n, int32_t k2_in, int32_t num_classes) {
     int tw, tn;
     const int tiles = wgrad_tiles(k2_in, num_classes, &tw, &tn);
     const int64_t nn = n > 0 ? n : 1;
-    return ((nn * kD2 + nn * num_classes + nn + 3) & ~(int64_t)3) + (int64_t)tiles * kSplits * (kTM * kTN) + tiles;
+    return (((int64_t)tiles + 3) & ~(int64_t)3) + (int64_t)tiles * kSplits * (kTM * kTN) +
+           ((nn * kD2 + nn * num_classes + nn + 3) & ~(int64_t)3);
 }
 
 namespace {
@@ -420,11 +424,11 @@ int head_plan(int32_t d1, int32_t d2, int32_t num_classes, int32_t n, bool sage,
     hp->K2 = sage ? 2 * d1 : d1;
     if (!gs_head_supported(d1, hp->K2, d2, num_classes)) return GS_ENOSUP;
     hp->tiles = wgrad_tiles(hp->K2, num_classes, &hp->tiles_w2, &hp->tn_w2);
-    hp->dz2 = ws;
+    hp->tickets = reinterpret_cast<int32_t*>(ws);                         // n-independent offsets first (see above)
+    hp->part = ws + (((int64_t)hp->tiles + 3) & ~(int64_t)3);
+    hp->dz2 = hp->part + (int64_t)hp->tiles * kSplits * (kTM * kTN);
     hp->dl = hp->dz2 + (int64_t)n * kD2;
     hp->loss_rows = hp->dl + (int64_t)n * num_classes;
-    hp->part = ws + (((int64_t)n * kD2 + (int64_t)n * num_classes + n + 3) & ~(int64_t)3);
-    hp->tickets = reinterpret_cast<int32_t*>(hp->part + (int64_t)hp->tiles * kSplits * (kTM * kTN));
     return GS_OK;
 }
 

@@ -15,14 +15,15 @@ constexpr int kWarps = 8;
 
 // pass 1: row lengths (degree, +1 if the node itself has to be appended)
 __global__ void __launch_bounds__(kWarps * 32)
-ragged_count_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+ragged_count_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int num_nodes,
                     const int32_t* __restrict__ nodes, int n, int add_self, int32_t* __restrict__ len) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (i >= n) return;
     const int32_t v = nodes[i];
-    const int64_t base = rowptr[v];
-    const int deg = (int)(rowptr[v + 1] - base);
+    const bool known = (unsigned)v < (unsigned)num_nodes;      // unknown id = isolated node (empty set in the reference)
+    const int64_t base = known ? rowptr[v] : 0;
+    const int deg = known ? (int)(rowptr[v + 1] - base) : 0;
     bool has = false;
     if (add_self)
         for (int j = lane; j < deg; j += 32) has |= (col[base + j] == v);
@@ -70,15 +71,16 @@ ragged_scan_kernel(const int32_t* __restrict__ len, int n, int32_t* __restrict__
 
 // pass 3: copy the rows (ascending, as stored) and append the node itself where needed
 __global__ void __launch_bounds__(kWarps * 32)
-ragged_fill_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+ragged_fill_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int num_nodes,
                    const int32_t* __restrict__ nodes, int n, const int32_t* __restrict__ off,
                    int32_t* __restrict__ flat) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (i >= n) return;
     const int32_t v = nodes[i];
-    const int64_t base = rowptr[v];
-    const int deg = (int)(rowptr[v + 1] - base);
+    const bool known = (unsigned)v < (unsigned)num_nodes;
+    const int64_t base = known ? rowptr[v] : 0;
+    const int deg = known ? (int)(rowptr[v + 1] - base) : 0;
     const int o = off[i], len = off[i + 1] - o;
     for (int j = lane; j < deg; j += 32) flat[o + j] = col[base + j];
     if (lane == 0 && len > deg) flat[o + deg] = v;
@@ -162,13 +164,13 @@ scatter_mean_ragged_kernel(const float* __restrict__ gout, int64_t ld_gout, int 
 
 }  // namespace
 
-extern "C" int gs_take_all_count(const int64_t* rowptr, const int32_t* col, const int32_t* nodes, int32_t n,
-                                 int32_t add_self, int32_t* len, int32_t* off, void* stream) {
-    if (n < 0 || !off) return GS_EINVAL;
+extern "C" int gs_take_all_count(const int64_t* rowptr, const int32_t* col, int32_t num_nodes, const int32_t* nodes,
+                                 int32_t n, int32_t add_self, int32_t* len, int32_t* off, void* stream) {
+    if (n < 0 || !off || num_nodes < 0) return GS_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     if (n > 0) {
         if (!rowptr || !col || !nodes || !len) return GS_EINVAL;
-        ragged_count_kernel<<<(n + kWarps - 1) / kWarps, kWarps * 32, 0, s>>>(rowptr, col, nodes, n, add_self, len);
+        ragged_count_kernel<<<(n + kWarps - 1) / kWarps, kWarps * 32, 0, s>>>(rowptr, col, num_nodes, nodes, n, add_self, len);
         GS_LAUNCH_CHECK();
     }
     ragged_scan_kernel<<<1, 1024, 0, s>>>(len, n, off);
@@ -176,11 +178,11 @@ extern "C" int gs_take_all_count(const int64_t* rowptr, const int32_t* col, cons
     return GS_OK;
 }
 
-extern "C" int gs_take_all_fill(const int64_t* rowptr, const int32_t* col, const int32_t* nodes, int32_t n,
-                                const int32_t* off, int32_t* flat, void* stream) {
+extern "C" int gs_take_all_fill(const int64_t* rowptr, const int32_t* col, int32_t num_nodes, const int32_t* nodes,
+                                int32_t n, const int32_t* off, int32_t* flat, void* stream) {
     if (n == 0) return GS_OK;
-    if (!rowptr || !col || !nodes || !off || !flat || n < 0) return GS_EINVAL;
-    ragged_fill_kernel<<<(n + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(rowptr, col, nodes, n, off, flat);
+    if (!rowptr || !col || !nodes || !off || !flat || n < 0 || num_nodes < 0) return GS_EINVAL;
+    ragged_fill_kernel<<<(n + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(rowptr, col, num_nodes, nodes, n, off, flat);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }

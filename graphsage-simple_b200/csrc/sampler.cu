@@ -30,7 +30,7 @@ __device__ __forceinline__ Philox philox4x32_10(uint32_t c0, uint32_t c1, uint32
 // reads -- three orders of magnitude below the feature gather it feeds, so the simple
 // mapping is the right one; the grid is sized from n_max and trimmed by *n_dev.
 __global__ void __launch_bounds__(128)
-sample_csr_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+sample_csr_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int num_nodes,
                   const int32_t* __restrict__ nodes, int n_max, const int32_t* __restrict__ n_dev,
                   int k, int width, int add_self, uint32_t seed_lo, uint32_t seed_hi,
                   int64_t step_imm, const int64_t* __restrict__ step_dev,
@@ -46,8 +46,10 @@ sample_csr_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
         return;
     }
     const int32_t v = nodes[i];
-    const int64_t base = rowptr[v];
-    const int deg = (int)(rowptr[v + 1] - base);
+    // ids outside [0, num_nodes) are isolated nodes (the reference's defaultdict(set) answers an empty set)
+    const bool known = (unsigned)v < (unsigned)num_nodes;
+    const int64_t base = known ? rowptr[v] : 0;
+    const int deg = known ? (int)(rowptr[v + 1] - base) : 0;
     const uint32_t step = (uint32_t)(step_dev ? *step_dev : step_imm);
     const uint32_t tag = i < n_head ? tag_head : tag_tail;
     int c = 0;
@@ -106,7 +108,7 @@ struct CsrPeers {
 template <bool PEER>
 __global__ void __launch_bounds__(kWarpRows * 32)
 sample_csr_warp_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const CsrPeers peers,
-                       const int32_t* __restrict__ nodes, int n_max, const int32_t* __restrict__ n_dev,
+                       int num_nodes, const int32_t* __restrict__ nodes, int n_max, const int32_t* __restrict__ n_dev,
                        int k, int width, int add_self, uint32_t seed_lo, uint32_t seed_hi,
                        int64_t step_imm, const int64_t* __restrict__ step_dev,
                        uint32_t tag_head, uint32_t tag_tail, int n_head,
@@ -130,8 +132,9 @@ sample_csr_warp_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
         rowptr = peers.rowptrs[owner];
         col = peers.cols[owner];
     }
-    const int64_t base = rowptr[r];
-    const int deg = (int)(rowptr[r + 1] - base);
+    const bool known = (unsigned)v < (unsigned)num_nodes;     // unknown id = isolated node: empty neighbour set
+    const int64_t base = known ? rowptr[r] : 0;
+    const int deg = known ? (int)(rowptr[r + 1] - base) : 0;
     int c;
     bool has_self = false;
     if (k < 0 || deg <= k) {
@@ -304,21 +307,20 @@ extern "C" int gs_sample_csr(const int64_t* rowptr, const int32_t* col, int32_t 
                              uint64_t seed, int64_t step, const int64_t* step_dev,
                              uint32_t tag_head, uint32_t tag_tail, int32_t n_head,
                              int32_t* idx, int32_t* cnt, void* stream) {
-    (void)num_nodes;
     if (n_max == 0) return GS_OK;       // empty frontier (e.g. nothing requested from this owner)
-    if (!rowptr || !col || !nodes || !idx || !cnt || n_max < 0 || width <= 0) return GS_EINVAL;
+    if (!rowptr || !col || !nodes || !idx || !cnt || n_max < 0 || width <= 0 || num_nodes < 0) return GS_EINVAL;
     if (k > kMaxK) return GS_ENOSUP;
     if (k >= 0 && width < k + (add_self ? 1 : 0)) return GS_EINVAL;
     if (n_max == 0) return GS_OK;
     if (k <= 32) {
         GS_PREFER_SMEM(sample_csr_warp_kernel<false>);
         sample_csr_warp_kernel<false><<<(n_max + kWarpRows - 1) / kWarpRows, kWarpRows * 32, 0, (cudaStream_t)stream>>>(
-            rowptr, col, CsrPeers{nullptr, nullptr, 1, 0}, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed,
+            rowptr, col, CsrPeers{nullptr, nullptr, 1, 0}, num_nodes, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed,
             (uint32_t)(seed >> 32), step, step_dev, tag_head, tag_tail, n_head, idx, cnt);
     } else {
         const int threads = 128;
         sample_csr_kernel<<<(n_max + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
-            rowptr, col, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed, (uint32_t)(seed >> 32),
+            rowptr, col, num_nodes, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed, (uint32_t)(seed >> 32),
             step, step_dev, tag_head, tag_tail, n_head, idx, cnt);
     }
     GS_LAUNCH_CHECK();
@@ -331,16 +333,15 @@ extern "C" int gs_sample_csr_peer(const int64_t* const* rowptrs, const int32_t* 
                                   uint64_t seed, int64_t step, const int64_t* step_dev,
                                   uint32_t tag_head, uint32_t tag_tail, int32_t n_head,
                                   int32_t* idx, int32_t* cnt, void* stream) {
-    (void)num_nodes;
     if (n_max == 0) return GS_OK;
-    if (!rowptrs || !cols || !nodes || !idx || !cnt || n_max < 0 || width <= 0) return GS_EINVAL;
+    if (!rowptrs || !cols || !nodes || !idx || !cnt || n_max < 0 || width <= 0 || num_nodes < 0) return GS_EINVAL;
     if (world < 1 || world > 16 || k > 32) return GS_ENOSUP;
     if (k >= 0 && width < k + (add_self ? 1 : 0)) return GS_EINVAL;
     int shift = -1;
     for (int b = 0; b < 5; ++b) if ((1 << b) == world) shift = b;
     GS_PREFER_SMEM(sample_csr_warp_kernel<true>);
     sample_csr_warp_kernel<true><<<(n_max + kWarpRows - 1) / kWarpRows, kWarpRows * 32, 0, (cudaStream_t)stream>>>(
-        nullptr, nullptr, CsrPeers{rowptrs, cols, world, shift}, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed,
+        nullptr, nullptr, CsrPeers{rowptrs, cols, world, shift}, num_nodes, nodes, n_max, n_dev, k, width, add_self, (uint32_t)seed,
         (uint32_t)(seed >> 32), step, step_dev, tag_head, tag_tail, n_head, idx, cnt);
     GS_LAUNCH_CHECK();
     return GS_OK;

@@ -58,8 +58,8 @@ SIGNATURES = {
     "gs_gather_mean_fwd_peer": (_i32, [_ptr, _i32, _i64, _i32, _ptr, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _ptr]),
     "gs_sample_csr_peer": (_i32, [_ptr, _ptr, _i32, _i32, _ptr, _i32, _ptr, _i32, _i32, _i32, _u64, _i64, _ptr,
                                   _u32, _u32, _i32, _ptr, _ptr, _ptr]),
-    "gs_take_all_count": (_i32, [_ptr, _ptr, _ptr, _i32, _i32, _ptr, _ptr, _ptr]),
-    "gs_take_all_fill": (_i32, [_ptr, _ptr, _ptr, _i32, _ptr, _ptr, _ptr]),
+    "gs_take_all_count": (_i32, [_ptr, _ptr, _i32, _ptr, _i32, _i32, _ptr, _ptr, _ptr]),
+    "gs_take_all_fill": (_i32, [_ptr, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _ptr]),
     "gs_gather_mean_ragged": (_i32, [_ptr, _i64, _i32, _ptr, _ptr, _i32, _ptr, _i64, _ptr]),
     "gs_scatter_mean_ragged": (_i32, [_ptr, _i64, _i32, _ptr, _ptr, _i32, _ptr, _i64, _ptr]),
     "gs_advance_step": (_i32, [_ptr, _ptr]),

@@ -48,7 +48,11 @@ class Encoder(nn.Module):
         """Device CSR of ``adj_lists`` (built on first use, shared between encoders that were
         given the same mapping object)."""
         if self._graph is None:
-            self._graph = graph_of(self.adj_lists, _device())
+            # rows of the feature table (when known): isolated trailing nodes get a CSR row too
+            n = getattr(self.features, "num_embeddings", None)
+            if n is None and getattr(self, "base_model", None) is not None and self.base_model.adj_lists is self.adj_lists:
+                n = self.base_model.graph.num_nodes
+            self._graph = graph_of(self.adj_lists, _device(), num_nodes=n)
         return self._graph
 
     @property

@@ -302,6 +302,7 @@ class TrainEngine:
         if not self.use_graphs:
             fn()
             return
+        key = key + (sampling.get_seed(),)         # the sampler seed is an immediate kernel argument baked into a capture
         g = self._graphs.get(key)
         if g is None:
             if key not in self._warm:          # first call eager: loads kernels, sets func attributes
@@ -607,6 +608,10 @@ def engine_for(model, batch):
     if eng is not None and eng.B >= batch and eng.k1 == model.enc.base_model.num_sample \
             and eng.k2 == model.enc.num_sample:
         return eng
+    if eng is not None:
+        # a larger batch / different fan-out replaces the engine: apply its deferred update and drop its queue first,
+        # so no weight update is lost (the new engine copies the weights out of the old flat block below)
+        eng.reset_pipeline()
     enc2 = model.enc
     enc1 = getattr(enc2, "base_model", None)
     if not (isinstance(enc2, Encoder) and isinstance(enc1, Encoder)):

@@ -43,7 +43,7 @@ class CSRGraph:
             nb = adj_lists[k]
             if len(nb):
                 hi = max(hi, max(int(x) for x in nb))
-        n = int(num_nodes) if num_nodes is not None else hi + 1
+        n = max(int(num_nodes), hi + 1) if num_nodes is not None else hi + 1
         deg = np.zeros(n + 1, dtype=np.int64)
         for k in keys:
             deg[k + 1] = len(adj_lists[k])
@@ -83,16 +83,19 @@ class CSRGraph:
 _GRAPH_CACHE = {}
 
 
-def graph_of(adj_lists, device="cuda"):
+def graph_of(adj_lists, device="cuda", num_nodes=None):
     """CSRGraph for an ``adj_lists`` mapping, converted once per object (the reference passes
     the same dict to every Encoder, model.py:219-221).  Mutating the mapping afterwards is
-    not tracked -- call ``forget(adj_lists)`` first."""
+    not tracked -- call ``forget(adj_lists)`` first.  ``num_nodes`` (rows of the feature table): the CSR gets a row
+    for every node of the table, also for isolated ones that appear in no edge (the reference's defaultdict(set)
+    answers those with an empty set, model.py:303); without it rows stop at the largest id seen in an edge, and the
+    kernels treat any id past that as isolated."""
     if isinstance(adj_lists, CSRGraph):
         return adj_lists
     hit = _GRAPH_CACHE.get(id(adj_lists))
-    if hit is not None and hit[0] is adj_lists:
+    if hit is not None and hit[0] is adj_lists and (num_nodes is None or hit[1].num_nodes >= int(num_nodes)):
         return hit[1]
-    g = CSRGraph.from_adj_lists(adj_lists, device=device)
+    g = CSRGraph.from_adj_lists(adj_lists, num_nodes=num_nodes, device=device)
     _GRAPH_CACHE[id(adj_lists)] = (adj_lists, g)
     return g
 

@@ -371,21 +371,22 @@ def sample_csr_peer(rowptr_ptrs, col_ptrs, world, num_nodes, nodes, k, add_self=
     return idx, cnt
 
 
-def take_all_csr(rowptr, col, nodes, add_self=False):
+def take_all_csr(rowptr, col, nodes, add_self=False, num_nodes=None):
     """Ragged full-neighbourhood tile of ``nodes`` -- see gs_take_all_count / gs_take_all_fill.
     Returns (off int32 [n+1], flat int32 [total]); one host read of the total."""
     lib = N.load()
     N.require_cuda(rowptr, col, nodes)
     n = nodes.shape[0]
     dev = nodes.device
+    num_nodes = rowptr.shape[0] - 1 if num_nodes is None else int(num_nodes)
     length = torch.empty(max(n, 1), device=dev, dtype=torch.int32)
     off = torch.empty(n + 1, device=dev, dtype=torch.int32)
-    N.check(lib.gs_take_all_count(N.ptr(rowptr), N.ptr(col), N.ptr(nodes), n, int(bool(add_self)), N.ptr(length),
-                                  N.ptr(off), N.stream()), "gs_take_all_count")
+    N.check(lib.gs_take_all_count(N.ptr(rowptr), N.ptr(col), num_nodes, N.ptr(nodes), n, int(bool(add_self)),
+                                  N.ptr(length), N.ptr(off), N.stream()), "gs_take_all_count")
     total = int(off[n].item())
     flat = torch.empty(max(total, 1), device=dev, dtype=torch.int32)[:total]
-    N.check(lib.gs_take_all_fill(N.ptr(rowptr), N.ptr(col), N.ptr(nodes), n, N.ptr(off), N.ptr(flat), N.stream()),
-            "gs_take_all_fill")
+    N.check(lib.gs_take_all_fill(N.ptr(rowptr), N.ptr(col), num_nodes, N.ptr(nodes), n, N.ptr(off), N.ptr(flat),
+                                 N.stream()), "gs_take_all_fill")
     LAUNCHES[0] += 3
     return off, flat
 

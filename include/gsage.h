@@ -60,6 +60,8 @@ GS_API const char* gs_strerror(int code);
  * key = seed); positions sorted, so tile entries ascend.  Rows i < n_head use tag_head,
  * the rest tag_tail (the reference's independent aggregator calls of one forward).
  * If step_dev != NULL the step is read from device memory (graph replay), else `step`.
+ * An id outside [0, num_nodes) is an isolated node: cnt = 0 (+ the node itself with add_self),
+ * as the reference's defaultdict(set) answers an empty set (model.py:303).
  * The exact specification is restated on the CPU in oracle/sampler_port.py.            */
 GS_API int gs_sample_csr(const int64_t* rowptr, const int32_t* col, int32_t num_nodes,
                   const int32_t* nodes, int32_t n_max, const int32_t* n_dev,
@@ -110,10 +112,10 @@ GS_API int gs_scatter_mean_bwd(const float* gout, int64_t ld_gout, int32_t neigh
  *   gs_take_all_fill:  flat[off[i] .. off[i+1]) = the row (ascending) [+ the node itself]
  *   gs_gather_mean_ragged:  out[i, :] = mean_e table[flat[e], :]        (zeros for empty rows)
  *   gs_scatter_mean_ragged: gtable[flat[e], :] += gout[i, :] / len(i)   (caller-zeroed gtable)        */
-GS_API int gs_take_all_count(const int64_t* rowptr, const int32_t* col, const int32_t* nodes, int32_t n,
-                      int32_t add_self, int32_t* len, int32_t* off, void* stream);
-GS_API int gs_take_all_fill(const int64_t* rowptr, const int32_t* col, const int32_t* nodes, int32_t n,
-                     const int32_t* off, int32_t* flat, void* stream);
+GS_API int gs_take_all_count(const int64_t* rowptr, const int32_t* col, int32_t num_nodes, const int32_t* nodes,
+                      int32_t n, int32_t add_self, int32_t* len, int32_t* off, void* stream);
+GS_API int gs_take_all_fill(const int64_t* rowptr, const int32_t* col, int32_t num_nodes, const int32_t* nodes,
+                     int32_t n, const int32_t* off, int32_t* flat, void* stream);
 GS_API int gs_gather_mean_ragged(const float* table, int64_t ld_table, int32_t dim, const int32_t* off,
                           const int32_t* flat, int32_t n, float* out, int64_t ld_out, void* stream);
 GS_API int gs_scatter_mean_ragged(const float* gout, int64_t ld_gout, int32_t dim, const int32_t* off,
@@ -189,8 +191,9 @@ GS_API int gs_classifier_xent(const float* h, int64_t ld_h, const float* wc, int
  *   gw2, gwc = weight gradients (overwritten; deterministic two-stage reduction)
  *   gh1 += d loss / d h1   (128-bit reductions into a caller-zeroed [*, d1] buffer)
  * with every gradient scaled by grad_scale.  Supported shapes: gs_head_supported() (d1 == d2 ==
- * 128, num_classes <= 128).  ws: gs_head_ws_floats() floats, 16-B aligned, ZEROED ONCE by the
- * caller before first use (it holds re-arming tickets).  logits may be NULL.                 */
+ * 128, num_classes <= 128).  ws: gs_head_ws_floats(n_max, ...) floats, 16-B aligned, ZEROED ONCE by
+ * the caller before first use (it holds re-arming tickets, at an offset that does not depend on n):
+ * one workspace sized for n_max serves every call with n <= n_max.  logits may be NULL.          */
 GS_API int gs_head_supported(int32_t d1, int32_t k2_in, int32_t d2, int32_t num_classes);
 GS_API int64_t gs_head_ws_floats(int32_t n, int32_t k2_in, int32_t num_classes);
 GS_API int gs_head_fwd_bwd(const float* h1, int64_t ld_h1, int32_t d1,

@@ -133,8 +133,8 @@ def test_host_helpers():
 
 
 def test_bench_reference_arm_prints_one_contract_line():
-    """`bench.py --impl reference` (the CPU arm: oracle port of the reference's dense-mask path on the host cores)
-    prints exactly one JSON line with the contract's keys, also when launched as rank 1 of a torchrun (no output)."""
+    """`bench.py --impl reference` (the CPU arm: the unmodified reference from oracle/_ref, or the oracle port of its
+    dense-mask path, on the host cores) prints exactly one JSON line with the contract's keys, also when launched as rank 1 of a torchrun (no output)."""
     import json
     import subprocess
     import sys
@@ -148,7 +148,50 @@ def test_bench_reference_arm_prints_one_contract_line():
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in j, key
-    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
+    from oracle import build_ref
+    kind = "reference" if build_ref.verify() else "port"        # oracle/_ref present (built here from /root/reference)?
+    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == kind
+    assert j["config"]["batch_per_gpu"] == 32 and j["config"]["global_batch"] == 32     # what the arm actually ran
     assert j["cpu_baseline"]["cores"] >= 1 and j["e2e"]["h2d_bytes_per_step"] == 0 and j["vs_baseline"] is None
+    if kind == "reference":                                      # the port stays available as a fallback
+        rp = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, GSAGE_REFERENCE_PORT="1"))
+        assert rp.returncode == 0 and json.loads(rp.stdout.strip())["cpu_baseline"]["kind"] == "port"
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_reference_copy_matches_oracle_port_bit_for_bit():
+    """oracle/_ref (the UNMODIFIED reference modules, oracle/build_ref.py) and the oracle port give the same loss and
+    the same post-SGD weights, bit for bit, for the same Python RNG state -- the pin of the port that also holds on
+    the GPU box, where /root/reference does not exist.  Skipped when oracle/_ref did not travel."""
+    import random
+    import numpy as np
+    import pytest
+    import torch
+    from oracle import build_ref, ref_path as R, ref_runtime as RR
+    if not build_ref.verify():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    rng = np.random.default_rng(0)
+    n, f = 400, 20
+    adj = {i: set() for i in range(n)}
+    for a, b in rng.integers(0, n, (3000, 2)):
+        adj[int(a)].add(int(b)); adj[int(b)].add(int(a))
+    table = torch.randn(n, f, generator=torch.Generator().manual_seed(0))
+    ws = [torch.randn(s, generator=torch.Generator().manual_seed(i)) * 0.1 for i, s in enumerate([(16, 2 * f), (16, 32), (5, 16)])]
+    labels = rng.integers(0, 5, (n, 1)).astype(np.int64)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = RR.build_two_layer(table, adj, f, 16, 16, 5, 4, 6, weights=ws)
+    opt = RR.make_optimizer(m, 0.7)
+    o = R.TwoLayerModel(table, adj, adj, 16, 16, 5, 4, 6, gcn=False, w1=ws[0].clone(), w2=ws[1].clone(), wc=ws[2].clone())
+    for step in range(3):
+        nodes = list(rng.integers(0, n, 64))
+        random.seed(3 + step)
+        l_ref = float(RR.train_step(m, opt, nodes, labels[np.array(nodes)]).detach())
+        random.seed(3 + step)
+        l_port = float(o.train_step(nodes, labels[np.array(nodes)], lr=0.7))
+        assert l_ref == l_port
+    assert torch.equal(m.enc.base_model.weight.detach(), o.enc1.weight.detach())
+    assert torch.equal(m.enc.weight.detach(), o.enc2.weight.detach()) and torch.equal(m.weight.detach(), o.weight.detach())
+    import graphsage                                            # the product package is still the one importable as `graphsage`
+    assert "graphsage-simple_b200" in graphsage.__file__

@@ -365,6 +365,42 @@ def test_fused_head_matches_fp64_reference(ops, n, sage, c, act, width):
     assert relerr(gh1.cpu().numpy(), H1.grad.numpy()) < REL
 
 
+@pytest.mark.parametrize("n_max,n_small,c", [(1024, 414, 3), (128, 100, 7), (512, 119, 41)])
+def test_fused_head_workspace_serves_smaller_batches(ops, n_max, n_small, c):
+    """ONE head workspace sized for the largest batch (what engine.py allocates) is used for B, then b < B
+    (the last partial batch of an epoch), then B again: the weight gradients of every call must equal those of a
+    call with a fresh exactly-sized workspace (round-1 bug: the re-arming tickets sat at an n-dependent offset)."""
+    rng = np.random.default_rng(5)
+    d1 = d2 = 128
+    k2, width = 2 * d1, 10
+    m = 4 * n_max
+    h1 = dev(rng.standard_normal((m, d1)).astype(np.float32))
+    w2 = dev((rng.standard_normal((d2, k2)) / np.sqrt(k2)).astype(np.float32))
+    wc = dev((rng.standard_normal((c, d2)) / np.sqrt(d2)).astype(np.float32))
+    shared = ops.head_ws(n_max, k2, c, "cuda")
+
+    def run(n, ws, seed):
+        r = np.random.default_rng(seed)
+        cnt = r.integers(1, width + 1, n).astype(np.int32)
+        idx = np.full((n, width), -1, dtype=np.int32)
+        for i in range(n):
+            idx[i, :cnt[i]] = np.sort(r.choice(np.arange(n, m), cnt[i], replace=False))
+        labels = r.integers(0, c, n).astype(np.int64)
+        comb2 = torch.zeros((n, k2), device="cuda"); h2 = torch.zeros((n, d2), device="cuda")
+        loss = torch.zeros(1, device="cuda"); gh1 = torch.zeros((m, d1), device="cuda")
+        gw2 = torch.full((d2, k2), 9.0, device="cuda"); gwc = ops.empty_rows(c, d2, "cuda", zero=True)
+        gwc.fill_(9.0)
+        ops.head_fwd_bwd(h1, d1, dev(idx), dev(cnt), dev(np.arange(n, dtype=np.int32)), w2, 1, wc, dev(labels), 1.0,
+                         comb2, h2, None, loss, gh1, gw2, gwc, ws)
+        return float(loss.item()), gw2.cpu().numpy().copy(), gwc.cpu().numpy().copy()
+
+    for seed, n in enumerate([n_max, n_small, n_max, n_small, 8, n_max]):
+        got = run(n, shared, seed)
+        want = run(n, ops.head_ws(n, k2, c, "cuda"), seed)
+        assert got[0] == want[0]
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]), (n, seed)
+
+
 @pytest.mark.parametrize("n,world,local", [(100000, 8, True), (1023, 2, False), (1025, 3, True), (1, 4, False), (5000, 1, True),
                                            (4096, 16, False)])
 def test_bucket_by_owner_bit_exact(ops, n, world, local):
@@ -378,6 +414,46 @@ def test_bucket_by_owner_bit_exact(ops, n, world, local):
     assert np.array_equal(send.cpu().numpy(), want)
     inv = np.empty(n, dtype=np.int64); inv[order] = np.arange(n)
     assert np.array_equal(perm.cpu().numpy(), inv)
+
+
+@pytest.mark.parametrize("k", [3, 40, None])
+def test_ids_past_the_last_csr_row_are_isolated_nodes(ops, k):
+    """A node that appears in no edge and whose id is above every id of the CSR (a trailing isolated node of the
+    feature table; the reference's defaultdict(set) answers set(), model.py:303) gets an empty tile row instead of
+    an out-of-bounds rowptr read -- warp kernel (k <= 32), thread kernel (k > 32), take-all and the ragged tiles."""
+    rng = np.random.default_rng(3)
+    n = 50
+    rowptr, col = random_csr(rng, n, 6)
+    nodes = np.array([0, n, 7, n + 100, 2 ** 31 - 1, 3], dtype=np.int32)
+    width = (k if k is not None else int(np.diff(rowptr).max())) + 1
+    idx, cnt = ops.sample_csr(dev(rowptr), dev(col), n, dev(nodes), k, add_self=True, seed=1, step=1, tag_head=1, width=width)
+    idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+    for i, v in enumerate(nodes):
+        if v >= n:
+            assert cnt[i] == 1 and idx[i, 0] == v and (idx[i, 1:] == -1).all()      # only the self loop
+    idx, cnt = ops.sample_csr(dev(rowptr), dev(col), n, dev(nodes), k, add_self=False, seed=1, step=1, tag_head=1, width=width)
+    assert (cnt.cpu().numpy()[[1, 3, 4]] == 0).all() and (idx.cpu().numpy()[[1, 3, 4]] == -1).all()
+    off, flat = ops.take_all_csr(dev(rowptr), dev(col), dev(nodes), add_self=False)
+    lens = np.diff(off.cpu().numpy())
+    assert (lens[[1, 3, 4]] == 0).all() and lens[0] == rowptr[1] - rowptr[0]
+
+
+def test_encoder_graph_covers_isolated_trailing_nodes():
+    """Encoder.graph sizes the CSR by the feature table, not by the largest id seen in an edge."""
+    import torch.nn as nn
+    from graphsage.aggregators import MeanAggregator
+    from graphsage.encoders import Encoder
+    from collections import defaultdict
+    adj = defaultdict(set)
+    for a, b in [(0, 1), (1, 2), (2, 3)]:
+        adj[a].add(b); adj[b].add(a)
+    emb = nn.Embedding(8, 4)
+    emb.weight = nn.Parameter(torch.arange(32, dtype=torch.float32).view(8, 4), requires_grad=False)
+    enc = Encoder(emb, 4, 3, adj, MeanAggregator(emb, cuda=True), num_sample=2, gcn=True, cuda=True)
+    assert enc.graph.num_nodes == 8
+    out = enc(torch.tensor([7, 3, 5]))                   # 5 and 7 are isolated: zero neighbour mean -> act(0)
+    assert out.shape == (3, 3) and torch.isfinite(out).all()
+    assert float(out[:, 0].abs().max()) == 0.0 and float(out[:, 2].abs().max()) == 0.0
 
 
 def test_encoder_tensor_core_repeatable(ops):
