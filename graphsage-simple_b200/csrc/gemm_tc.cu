@@ -538,7 +538,9 @@ int grid1d(int64_t total) {
 }  // namespace
 
 extern "C" int gs_encoder_tc_supported(int32_t k_in, int32_t d_out) {
-    return (d_out == kTile && k_in >= kChunk && (k_in & 3) == 0) ? 1 : 0;
+    // any k_in >= one chunk: the tensor maps carry the true column count, so the tail of the last K chunk (and a k_in
+    // that is not a multiple of 4, e.g. Citeseer's 3703 words) is zero-filled by TMA on both operands
+    return (d_out == kTile && k_in >= kChunk) ? 1 : 0;
 }
 
 // floats of workspace for the forward: W_hi + W_lo
