@@ -253,6 +253,7 @@ def workload_config(args, batch):
                 "inside the gather / sampler kernels" if getattr(args, "partitioned", False) else "graph + features replicated",
                 getattr(args, "dp_mode", "none")),
             "l2_policy": "inputs larger than L2: 561 MB feature table, fresh random targets every step",
+            "device_loop": getattr(args, "device_loop", None),
             "lr": args.lr}
 
 
@@ -349,7 +350,7 @@ def run_b200(args):
     # device-resident inputs: one pre-packed staging block [sampler step | labels | targets] per batch of the
     # pool, already in HBM; a step's staging is ONE device-to-device copy of 12 KB
     warm = W + 10              # every graph variant (4 frontier-set rotations x eager, capture) is replaying before the timed loop
-    total = warm + K + 2
+    total = warm + K + 2 + 16
     d_blocks = torch.stack([eng.pack_stage(pool_nodes[i % pool], pool_labels[i % pool], i + 1)
                             for i in range(total)]).to(dev)
     eng.push(None, None, None, packed=(d_blocks[0], B))
@@ -363,13 +364,42 @@ def run_b200(args):
         old = step_done.pop(i - 2, None)
         if old is not None:
             old.synchronize()
-        eng.push(None, None, None, packed=(d_blocks[i + 2], B))
+        eng.push(None, None, None, packed=(d_blocks[(i + 2) % total], B))
         eng.step_pipelined(lr, allreduce)
         step_done[i] = torch.cuda.Event()
         step_done[i].record()
 
+    # Device-resident loop, K_MULTI steps per graph launch: the staging of a step's inputs is gs_stage_next (block index
+    # read from a device cursor), so K_MULTI whole pipelined steps -- each still one stage + sample chain, one gather,
+    # one compute chain, one SGD / all-reduce -- replay as ONE captured graph; the per-step host work (two launches
+    # per rank, 8 ranks on 16 host cores, each waiting for the slowest rank's flags every step) is paid once per
+    # K_MULTI steps.  GSAGE_BENCH_MULTI=0 restores one launch per step.
+    k_multi = int(os.environ.get("GSAGE_BENCH_MULTI", "4")) if allreduce is None else 0
+    k_multi -= k_multi % eng.slots
+    cursor = torch.zeros(1, dtype=torch.int64, device=dev)
+    multi_done = []
+
+    def device_multi(i):
+        """steps i .. i + k_multi - 1"""
+        if len(multi_done) >= 2:
+            multi_done.pop(0).synchronize()
+        eng.run_device_queue(d_blocks, cursor, k_multi, lr)
+        ev = torch.cuda.Event()
+        ev.record()
+        multi_done.append(ev)
+
+    n_single = K % k_multi if k_multi else K
+    n_multi = (K - n_single) // k_multi if k_multi else 0
     for i in range(warm):                  # includes the eager + capture iterations of every rotation
         device_step(i)
+    i_next = warm
+    if n_multi:
+        torch.cuda.synchronize()
+        step_done.clear()
+        for _ in range(3):                 # eager run, capture + replay, replay
+            cursor.fill_((i_next + 2) % total)
+            device_multi(i_next)
+            i_next += k_multi
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -377,14 +407,24 @@ def run_b200(args):
     clocks.start()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    multi_done.clear()
+    if n_multi:
+        cursor.fill_((i_next + 2) % total)
     ev0.record()
-    for i in range(K):
-        device_step(warm + i)
+    for _ in range(n_multi):
+        device_multi(i_next)
+        i_next += k_multi
+    for _ in range(n_single):
+        device_step(i_next)
+        i_next += 1
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
+    args.device_loop = ("%d graph launches of %d pipelined steps each (inputs staged from a device-resident pool by "
+                        "gs_stage_next) + %d single-step launches" % (n_multi, k_multi, n_single)) if n_multi else \
+        "one graph launch per step"
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -272,12 +272,13 @@ class TrainEngine:
         else:
             ops.sgd_step(self.flat_w, self.flat_g, lr)
 
-    def _overlapped(self, p, b0, b1, b2, lr, lead_lr=None):
+    def _overlapped(self, p, b0, b1, b2, lr, lead_lr=None, stage=None):
         """One pipelined step as a fork/join over three streams (captured as ONE CUDA graph):
         compute chain of set p on the current stream || gather of set p+1 || sample chain of set
         p+2.  b1 / b2 are None when the queue is shorter (tail of a run).  ``lead_lr``: apply the
         PREVIOUS step's deferred update first (data parallel, see step_pipelined); ``lr=None``: leave
-        this step's update to the next call."""
+        this step's update to the next call.  ``stage=(pool, cursor)``: the inputs of the batch that is sampled in
+        this step are taken from a device-resident pool by gs_stage_next (run_device_queue)."""
         main = torch.cuda.current_stream()
         if b1 is not None:
             self._gstream.wait_stream(main)
@@ -286,6 +287,8 @@ class TrainEngine:
         if b2 is not None:
             self._sstream.wait_stream(main)
             with torch.cuda.stream(self._sstream):
+                if stage is not None:
+                    ops.stage_next(stage[0], stage[1], self.sets[(p + 2) % self.slots].stage_dev)
                 self._sample_chain(self.sets[(p + 2) % self.slots], b2)
         if lead_lr is not None:
             self._update(lead_lr)
@@ -322,7 +325,7 @@ class TrainEngine:
     def launches_per_step(self):
         """Kernels of libgsage_sm100.so in one train step (fwd+bwd+SGD), counted when enqueued."""
         c = self._launch_count
-        whole = [v for k, v in c.items() if k[0] in ("step", "pipe")]
+        whole = [v for k, v in c.items() if k[0] in ("step", "pipe")] + [v // k[3] for k, v in c.items() if k[0] == "multi"]
         if whole:
             return max(whole)
         parts = sum(max([v for k, v in c.items() if k[0] == nm] or [0]) for nm in ("s", "g", "cchain"))
@@ -537,6 +540,37 @@ class TrainEngine:
         done.record()                                 # set p may be restaged once this step has finished
         self._slot_done[p] = done
         self.cur = (p + 1) % self.slots
+
+    def run_device_queue(self, pool, cursor, k, lr):
+        """``k`` pipelined steps (a multiple of ``slots``) as ONE graph replay, for inputs that already live in HBM:
+        ``pool`` [n_blocks, stage bytes] uint8 holds pre-packed staging blocks (``pack_stage``), ``cursor`` (int64
+        device scalar) the index of the next block to stage.  Every step is exactly a ``step_pipelined`` step in its
+        steady state -- SGD / all-reduce of the previous batch, compute chain of batch t || feature gather of t+1 ||
+        [stage + sample chain] of t+2 -- only the per-step host work (a staging copy and a graph launch per step,
+        from every rank of a data-parallel job) is paid once per ``k`` steps.  Needs the steady state of the
+        streaming mode: two full batches queued (gathered, sampled) and the previous update deferred."""
+        q = self.queue
+        if k <= 0 or k % self.slots:
+            raise ValueError("run_device_queue: k must be a positive multiple of %d" % self.slots)
+        if len(q) != 2 or q[0]["state"] != 2 or q[1]["state"] != 1 or q[0]["b"] != q[1]["b"] or self._pending_lr is None:
+            raise RuntimeError("run_device_queue needs the pipeline's steady state (run step_pipelined first)")
+        if float(lr) != self._pending_lr:
+            raise ValueError("run_device_queue: lr differs from the deferred update's lr")
+        b, p0 = q[0]["b"], self.cur
+        assert q[0]["slot"] == p0 and pool.shape[1] == self.sets[0].stage_dev.numel()
+        main_stream = torch.cuda.current_stream()
+        for e in q:
+            if e["staged"] is not None:
+                main_stream.wait_event(e["staged"])
+                e["staged"] = None
+        if self._cstream is not None:
+            main_stream.wait_stream(self._cstream)
+
+        def body():
+            for j in range(k):
+                self._overlapped((p0 + j) % self.slots, b, b, b, None, float(lr), stage=(pool, cursor))
+        self._run(("multi", p0, b, k, float(lr), pool.data_ptr(), cursor.data_ptr()), body)
+        self._slot_done = [None] * self.slots         # later pushes order themselves after everything enqueued so far
 
     def read_loss(self):
         self.loss_host.copy_(self.loss, non_blocking=True)

@@ -412,3 +412,12 @@ def scatter_mean_ragged(gout, dim, off, flat, gtable):
 def advance_step(step_dev):
     N.check(N.load().gs_advance_step(N.ptr(step_dev), N.stream()), "gs_advance_step")
     LAUNCHES[0] += 1
+
+
+def stage_next(pool, cursor, dst):
+    """dst <- pool[*cursor % len(pool)]; ++*cursor  (device-side batch queue, see gs_stage_next)."""
+    N.require_cuda(pool, cursor, dst)
+    assert pool.dim() == 2 and pool.is_contiguous() and pool.dtype == torch.uint8 and dst.numel() == pool.shape[1]
+    N.check(N.load().gs_stage_next(N.ptr(pool), pool.shape[1], pool.shape[0], N.ptr(cursor), N.ptr(dst), N.stream()),
+            "gs_stage_next")
+    LAUNCHES[0] += 1

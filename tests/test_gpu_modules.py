@@ -299,6 +299,67 @@ def test_pipelined_prefetch_equals_sequential_steps(golden, gcn):
     assert out["seq"][0][0] != out["seq"][0][-1]
 
 
+@pytest.mark.parametrize("wide", [False, True])
+def test_device_queue_multi_step_graph_equals_single_steps(golden, wide):
+    """engine.run_device_queue (k pipelined steps + their gs_stage_next staging as ONE captured graph, the loop
+    bench.py times for `value`) gives the same losses and weights as k single step_pipelined calls."""
+    from graphsage import sampling
+    from graphsage.engine import engine_for
+    rng = np.random.default_rng(17)
+    if wide:
+        n, f, c, k1, k2, B = 1200, 100, 9, 5, 7, 64
+        adj = {v: set() for v in range(n)}
+        for a, b in rng.integers(0, n, (8 * n, 2)):
+            adj[int(a)].add(int(b)); adj[int(b)].add(int(a))
+        gg = {"table": rng.standard_normal((n, f)).astype(np.float32),
+              "w1": (rng.standard_normal((128, 2 * f)) / np.sqrt(2 * f)).astype(np.float32),
+              "w2": (rng.standard_normal((128, 256)) / 16).astype(np.float32),
+              "wc": (rng.standard_normal((c, 128)) / 11).astype(np.float32)}
+        labels_all = rng.integers(0, c, n).astype(np.int64)
+    else:
+        g = golden("model_live")
+        gg = dict(g, w1=g["sage_w1"], w2=g["sage_w2"], wc=g["sage_wc"])
+        adj = csr_to_adj(g["rowptr"], g["col"])
+        k1, k2, B = int(g["k1"]), int(g["k2"]), 32
+        n = len(g["rowptr"]) - 1
+        labels_all = g["labels"].reshape(-1)
+    T, lr = 9, 0.05                                       # 1 single step to reach the steady state + 2 graphs of 4
+    batches = [rng.permutation(n)[:B] for _ in range(T + 2)]
+    out = {}
+    for mode in ("single", "multi"):
+        model, enc1, enc2 = build_model(gg, False, adj, adj, k1, k2)
+        sampling.seed(5)
+        eng = engine_for(model, B)
+        blocks = torch.stack([eng.pack_stage(b, labels_all[b], i + 1) for i, b in enumerate(batches)]).cuda()
+        eng.reset_pipeline()
+        eng.push(None, None, None, packed=(blocks[0], B))
+        eng.push(None, None, None, packed=(blocks[1], B))
+        losses = []
+
+        def single(i):
+            eng.push(None, None, None, packed=(blocks[i + 2], B))
+            eng.step_pipelined(lr)
+            losses.append(float(eng.loss.item()))
+        if mode == "single":
+            for i in range(T):
+                single(i)
+        else:
+            single(0)
+            cursor = torch.tensor([3], dtype=torch.int64, device="cuda")
+            for rep in range(2):
+                eng.run_device_queue(blocks, cursor, 4, lr)
+                losses.append(float(eng.loss.item()))
+            assert int(cursor.item()) == 3 + 8 and any(k[0] == "multi" for k in eng._launch_count)
+        eng.flush_update()
+        torch.cuda.synchronize()
+        out[mode] = (losses, [p.detach().cpu().numpy().copy() for p in (model.weight, enc2.weight, enc1.weight)])
+    assert out["single"][0][0] == out["multi"][0][0]
+    assert abs(out["single"][0][4] - out["multi"][0][1]) <= REL * abs(out["single"][0][4])     # loss of step 4
+    assert abs(out["single"][0][8] - out["multi"][0][2]) <= REL * abs(out["single"][0][8])     # loss of step 8
+    for a, b in zip(out["single"][1], out["multi"][1]):
+        assert relerr(b, a) < REL
+
+
 @pytest.mark.parametrize("gcn,feat,batch", [(False, 64, 96), (True, 36, 33), (False, 602, 256)])
 def test_fused_engine_wide_layers_equal_op_by_op_path(gcn, feat, batch):
     """Hidden width 128/128 (the BASELINE configs): the engine takes the tcgen05 layer-1 GEMMs and the
