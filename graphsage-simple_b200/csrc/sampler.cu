@@ -303,11 +303,11 @@ __global__ void advance_step_kernel(int64_t* step) { *step += 1; }
 // frontier set's staging area and advance the cursor -- what lets several train steps sit in ONE captured graph
 // (the source of a captured memcpy is fixed at capture time; this kernel reads it from device memory).
 __global__ void __launch_bounds__(256)
-stage_next_kernel(const uint4* __restrict__ pool, int64_t block_u4, int64_t n_blocks, int64_t* cursor,
-                  uint4* __restrict__ dst) {
+stage_next_kernel(const uint32_t* __restrict__ pool, int64_t block_words, int64_t n_blocks, int64_t* cursor,
+                  uint32_t* __restrict__ dst) {
     const int64_t cur = *reinterpret_cast<volatile int64_t*>(cursor);
-    const uint4* src = pool + (cur % n_blocks) * block_u4;
-    for (int64_t i = threadIdx.x; i < block_u4; i += blockDim.x) dst[i] = src[i];
+    const uint32_t* src = pool + (cur % n_blocks) * block_words;
+    for (int64_t i = threadIdx.x; i < block_words; i += blockDim.x) dst[i] = src[i];
     __syncthreads();
     if (threadIdx.x == 0) *cursor = cur + 1;
 }
@@ -396,10 +396,10 @@ extern "C" int gs_dedup_remap(int32_t* idx, const int32_t* cnt, int32_t n_max, c
 extern "C" int gs_stage_next(const void* pool, int64_t block_bytes, int64_t n_blocks, int64_t* cursor, void* dst,
                              void* stream) {
     if (!pool || !cursor || !dst || block_bytes <= 0 || n_blocks <= 0) return GS_EINVAL;
-    if ((block_bytes & 15) || !gs_aligned16(pool) || !gs_aligned16(dst)) return GS_EALIGN;
+    if ((block_bytes & 3) || (reinterpret_cast<uintptr_t>(pool) & 3) || (reinterpret_cast<uintptr_t>(dst) & 3)) return GS_EALIGN;
     GS_PREFER_SMEM(stage_next_kernel);
-    stage_next_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(pool), block_bytes / 16, n_blocks,
-                                                          cursor, reinterpret_cast<uint4*>(dst));
+    stage_next_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(pool), block_bytes / 4, n_blocks,
+                                                          cursor, reinterpret_cast<uint32_t*>(dst));
     GS_LAUNCH_CHECK();
     return GS_OK;
 }

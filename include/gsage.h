@@ -282,7 +282,7 @@ GS_API int gs_sample_csr_peer(const int64_t* const* rowptrs, const int32_t* cons
 /* Small device-side helpers used to keep a training step free of host round trips.       */
 GS_API int gs_advance_step(int64_t* step_dev, void* stream);                    /* ++*step_dev   */
 /* Device-side batch queue for inputs that already live in HBM: dst[0..block_bytes) = block (*cursor % n_blocks) of
- * `pool` (n_blocks blocks of block_bytes, 16-B multiples, 16-B aligned), then ++*cursor.  One staging block holds what
+ * `pool` (n_blocks blocks of block_bytes, a multiple of 4, 4-B aligned), then ++*cursor.  One staging block holds what
  * the reference's loop fetches per minibatch (model.py:243-248: the batch's node ids and labels) plus the sampler step;
  * reading the block index from device memory lets several train steps replay as ONE captured graph.               */
 GS_API int gs_stage_next(const void* pool, int64_t block_bytes, int64_t n_blocks, int64_t* cursor, void* dst,
