@@ -16,9 +16,14 @@
 // the shared-memory read traffic of the MMAs, which (not the tensor pipe) bounded the first
 // version of this kernel (profiles/README.md, r01 tc_gemm v1 vs v2).
 //
+// SAGE concat in place (graphsage/encoders.py:53-56 `cat([self.features(nodes), neigh_feats])`): when X is
+// [table[self_ids] | mean], only the mean half exists in memory; the producer warp gathers the self rows straight
+// from the feature table with coalesced 16-B cp.async (LDGSTS) into the same swizzled stage ring, so the self half of
+// the combined tile is never written or re-read through HBM (gs_sage_encoder_fwd_tc / gs_sage_encoder_wgrad_tc).
+//
 // Per CTA (320 threads, 1 CTA/SM): 3-stage smem ring of 48 KB (X raw, Y_hi, Y_lo), TMEM =
 // 2 main accumulators + 1 correction accumulator (3 x 128 columns) + 2 A slots (2 x 64 columns).
-//   warp 0      TMA producer
+//   warp 0      producer: TMA tiles (one lane) + gathered table rows (cp.async spread over the lanes)
 //   warps 2..5  splitter (smem -> registers -> TMEM A slot), later the epilogue
 //   warp 1      MMA issuer (one lane): per stage 4 k-steps x 3 tcgen05.mma, tcgen05.commit
 #include <cuda.h>
@@ -37,7 +42,8 @@ constexpr int kStages = GS_TC_STAGES;
 constexpr int kTile = 128;            // M and N of the UMMA tile (d_out == 128)
 constexpr int kChunk = 32;            // reduction elements per stage: 32 fp32 = one 128-B swizzle row
 constexpr int kOperandBytes = kTile * kChunk * 4;          // 16 KB
-constexpr int kStageBytes = 3 * kOperandBytes;             // X raw, Y_hi, Y_lo (pre-split in global memory)
+constexpr int kXBytes = kOperandBytes;
+constexpr int kStageBytes = kXBytes + 2 * kOperandBytes;   // X raw, Y_hi, Y_lo (pre-split in global memory)
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers + tmem slot*/;
 constexpr int kThreads = 320;          // TMA, MMA, 2 x 4 X-splitter/epilogue warps
 // The tensor core rounds toward zero when it adds a k-step into the fp32 accumulator: measured
@@ -77,30 +83,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
 }
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+// Gathered feature rows: 16-B cp.async (LDGSTS, L2-only) straight into the stage, completion counted on the stage's
+// full barrier; src_bytes = 0 zero-fills the 16 bytes.  Measured (profiles/README.md, round 2): one issuing warp pays
+// ~45-50 cycles per LDGSTS (32 per chunk = the whole chunk period) and ~55 cycles per 1-D bulk copy (UBLKCP; 128 per
+// chunk made the forward 2.9x slower), so the in-place concat is correct but SLOWER than reading a materialised tile:
+// it stays an option (GSAGE_SPLIT_SELF=1), not the default.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes));
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {      // arrives once this thread's copies have landed
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 // Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 format (version 1).
@@ -142,6 +140,15 @@ struct TcArgs {
     int64_t ld_out;
     int rows_per_split;        // TN only (multiple of kChunk)
     int64_t split_stride;      // TN only
+    // SAGE concat consumed in place: X = [table[self_ids] | mean].  The self half is never materialised: the
+    // producer warp gathers the rows straight from the feature table (graphsage/encoders.py:53 `self.features(nodes)`
+    // + the cat of :56) with 1-D bulk copies.  NT: the first self_units K chunks; TN: the first self_units column tiles.
+    const float* table;        // nullptr: X is one dense matrix (map_x), self_units == 0
+    int64_t ld_table;
+    const int32_t* self_ids;   // [n_max] table row of every X row
+    int self_units;
+    int self_cols;             // feature width F (columns of the self half; the mean half follows at column F of W / dW)
+    int prefetch;              // gathered rows are pulled into L2 this many chunks ahead of the ring
     int debug;                 // experiment switches (GSAGE_TC_DEBUG), 0 in production
     long long* trace;          // optional [64 chunks][16 events] clock64 trace of block 0 (GSAGE_TC_TRACE)
 };
@@ -155,18 +162,6 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-        ::"r"(taddr),
-          "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
 }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -200,10 +195,14 @@ constexpr int kBarAccum = 2 * kStages + 2 * kASlots;
 constexpr int kBarYReady = kBarAccum + 1;         // [kStages]  Y tile split into hi/lo in shared memory
 
 // 72 registers: 320 x 72 = 23 K leaves room for the gather blocks that share the SM (gather.cu)
+//   map_x          dense part of X: the whole X, or its mean half [n, k_in] when the self half is gathered
+//   map_yhi/ylo    NT: W_hi / W_lo columns of the dense part;  TN: dZ_hi / dZ_lo
+//   map_shi/slo    NT only: W_hi / W_lo columns of the self half (columns [0, self_cols) of W)
 template <bool TN>
 __global__ void __maxnreg__(72)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_yhi,
-               const __grid_constant__ CUtensorMap map_ylo, TcArgs g) {
+               const __grid_constant__ CUtensorMap map_ylo, const __grid_constant__ CUtensorMap map_shi,
+               const __grid_constant__ CUtensorMap map_slo, TcArgs g) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + kStages * kStageBytes;
@@ -212,24 +211,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int n = gs_row_count(g.n_max, g.n_dev);
-    int chunk_begin, chunk_end, x_fixed;
+    // NT: chunks [0, self_chunks) take X from the table (gathered rows), the rest from map_x.
+    // TN: column tiles [0, self_units) take X from the table, the rest from map_x; chunks run over rows.
+    int chunk_begin, chunk_end, x_fixed, self_chunks = 0;
+    bool self_tile = false;             // TN: this CTA's column tile lies in the self half
+    int out_col0 = 0, col_limit = g.k_in;
     if (!TN) {
         x_fixed = blockIdx.x * kTile;                          // first row of this tile
         if (x_fixed >= n) return;
+        self_chunks = g.self_units;
         chunk_begin = 0;
-        chunk_end = (g.k_in + kChunk - 1) / kChunk;            // over columns of X
+        chunk_end = self_chunks + (g.k_in + kChunk - 1) / kChunk;   // over columns of [self | dense]
     } else {
-        x_fixed = blockIdx.x * kTile;                          // first column of this tile
+        self_tile = (int)blockIdx.x < g.self_units;
+        x_fixed = (self_tile ? blockIdx.x : blockIdx.x - g.self_units) * kTile;   // first column of this tile (in its half)
+        if (self_tile) col_limit = g.self_cols; else out_col0 = g.table ? g.self_cols : 0;
         const int r0 = blockIdx.y * g.rows_per_split;
         const int r1 = min(n, r0 + g.rows_per_split);
         chunk_begin = r0 / kChunk;
         chunk_end = r1 > r0 ? (r1 + kChunk - 1) / kChunk : chunk_begin;   // over rows of X
     }
     const int nchunks = chunk_end - chunk_begin;
+    const bool gathers = TN ? self_tile : self_chunks > 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(bars + 8 * (kBarFull + s), 1);           // producer's expect_tx arrive
+            // producer's expect_tx arrive; with gathered rows every producer lane arrives once more (its cp.async group)
+            mbar_init(bars + 8 * (kBarFull + s), gathers ? 33 : 1);
             mbar_init(bars + 8 * (kBarEmpty + s), 1);          // tcgen05.commit
         }
         for (int a = 0; a < kASlots; ++a) {
@@ -251,38 +259,115 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t tmem_a = tmem + kAccs * kTile;              // first A-staging column
 
     if (warp == 0) {
-        // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c % kStages, it = c / kStages;
-                mbar_wait(bars + 8 * (kBarEmpty + s), (it & 1) ^ 1);
-                TC_TRACE(0, c);
-                const uint32_t st = base + s * kStageBytes;
-                const uint32_t full = bars + 8 * (kBarFull + s);
-                const int kc = (chunk_begin + c) * kChunk;
-                if (g.debug & 8) { mbar_arrive(full); continue; }
-                mbar_expect_tx(full, 3 * kOperandBytes);
-                if (!TN) {
-                    tma_load_2d(st, &map_x, kc, x_fixed, full);                           // X rows (SW128)
-                    tma_load_2d(st + kOperandBytes, &map_yhi, kc, 0, full);               // W_hi (SW128, K-major)
-                    tma_load_2d(st + 2 * kOperandBytes, &map_ylo, kc, 0, full);           // W_lo
-                } else {
-                    tma_load_2d(st, &map_x, x_fixed, kc, full);                           // X [32 rows][128 cols], linear
+        // ---------------------------------------------------------------- producer (TMA tiles + gathered rows)
+        // The whole warp runs the loop: a gathered chunk is 32 coalesced 16-B cp.async per lane.
+        const int64_t ld_t = g.ld_table;
+        int my_rows[kTile / 32];                               // NT: table rows lane, lane + 32, ... of this tile
+        if (!TN && gathers) {
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {                                         // dZ in 32-column blocks
-                        tma_load_2d(st + kOperandBytes + b * 4096, &map_yhi, 32 * b, kc, full);
-                        tma_load_2d(st + 2 * kOperandBytes + b * 4096, &map_ylo, 32 * b, kc, full);
+            for (int i = 0; i < kTile / 32; ++i) {
+                const int r = x_fixed + lane + 32 * i;
+                my_rows[i] = __ldg(g.self_ids + (r < n ? r : n - 1));        // rows past n: any valid row (never stored)
+            }
+        }
+        // Gathered rows are random 128-B (NT) / 512-B (TN) pieces of the table in HBM: each chunk's pieces are pulled
+        // into L2 `pf` chunks before the ring asks for them, so the ring's cp.async see L2 latency
+        const int pf = gathers ? g.prefetch : 0;
+        auto prefetch_chunk = [&](int c) {
+            if (!TN) {
+                if (c >= self_chunks) return;
+                const int col = c * kChunk;
+                if (col >= (int)ld_t) return;
+                const int last = min(col + kChunk, (int)ld_t) - 1;
+#pragma unroll
+                for (int i = 0; i < kTile / 32; ++i) {
+                    const float* row = g.table + (int64_t)my_rows[i] * ld_t;
+                    prefetch_l2(row + col);
+                    prefetch_l2(row + last);                   // rows are not 128-B aligned: a piece may straddle two lines
+                }
+            } else {
+                const int r = (chunk_begin + c) * kChunk + lane;
+                if (c >= nchunks || r >= n) return;
+                const float* row = g.table + (int64_t)__ldg(g.self_ids + r) * ld_t + x_fixed;
+                const int w = min(kTile, (int)ld_t - x_fixed);
+                for (int o = 0; o < w; o += 32) prefetch_l2(row + o);
+                prefetch_l2(row + w - 1);
+            }
+        };
+        for (int c = 0; c < pf; ++c) prefetch_chunk(c);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % kStages, it = c / kStages;
+            if (pf) prefetch_chunk(c + pf);
+            mbar_wait(bars + 8 * (kBarEmpty + s), (it & 1) ^ 1);
+            TC_TRACE(0, c);
+            const uint32_t st = base + s * kStageBytes;
+            const uint32_t full = bars + 8 * (kBarFull + s);
+            if (g.debug & 8) { if (lane == 0 || gathers) mbar_arrive(full); if (lane == 0 && gathers) mbar_arrive(full); continue; }
+            if (!TN) {
+                if (c < self_chunks) {
+                    // 128 table rows x 128 B in the SWIZZLE_128B layout the TMA tiles have: 16-B piece p of row r at
+                    // r * 128 + ((p ^ (r % 8)) * 16).  Lanes 8s..8s+7 copy the 8 pieces of one row (one 128-B line).
+                    const int col = c * kChunk;
+                    if (lane == 0) {
+                        mbar_expect_tx(full, 2 * kOperandBytes);
+                        tma_load_2d(st + kXBytes, &map_shi, col, 0, full);                 // W_hi, self columns
+                        tma_load_2d(st + kXBytes + kOperandBytes, &map_slo, col, 0, full); // W_lo
+                    }
+                    const int piece = lane & 7, sub = lane >> 3;
+                    const uint32_t src_bytes = (col + 4 * piece < (int)ld_t) ? 16u : 0u;   // past the row: zero-fill
+                    const float* src0 = g.table + (src_bytes ? col + 4 * piece : 0);
+#pragma unroll
+                    for (int i = 0; i < kTile / 4; ++i) {
+                        const int r = 4 * i + sub;
+                        const int id = __shfl_sync(0xffffffffu, my_rows[i / 8], 4 * (i % 8) + sub);
+                        cp_async16(st + (uint32_t)(r * 128 + ((piece ^ (r & 7)) << 4)), src0 + (int64_t)id * ld_t, src_bytes);
+                    }
+                    cp_async_arrive(full);
+                } else {
+                    if (lane == 0) {
+                        const int kc = (c - self_chunks) * kChunk;
+                        mbar_expect_tx(full, 3 * kOperandBytes);
+                        tma_load_2d(st, &map_x, kc, x_fixed, full);                        // X rows (SW128)
+                        tma_load_2d(st + kXBytes, &map_yhi, kc, 0, full);                  // W_hi (SW128, K-major)
+                        tma_load_2d(st + kXBytes + kOperandBytes, &map_ylo, kc, 0, full);  // W_lo
+                    }
+                    if (gathers) mbar_arrive(full);            // keeps the per-chunk arrival count uniform (33)
+                }
+            } else {
+                const int kc = (chunk_begin + c) * kChunk;
+                if (lane == 0) {
+                    mbar_expect_tx(full, (self_tile ? 2 : 3) * kOperandBytes);
+                    if (!self_tile) tma_load_2d(st, &map_x, x_fixed, kc, full);            // X [32 rows][128 cols], linear
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {                                          // dZ in 32-column blocks
+                        tma_load_2d(st + kXBytes + b * 4096, &map_yhi, 32 * b, kc, full);
+                        tma_load_2d(st + kXBytes + kOperandBytes + b * 4096, &map_ylo, 32 * b, kc, full);
                     }
                 }
-                TC_TRACE(1, c);
+                if (self_tile) {
+                    // row kc + i of X = table row self_ids[kc + i], columns [x_fixed, x_fixed + 128): instruction i copies
+                    // one row's 512 contiguous bytes (lane = 16-B piece) into the linear [32][128] tile
+                    const int r = kc + lane;
+                    const int my_id = __ldg(g.self_ids + (r < n ? r : n - 1));             // rows past n meet dZ rows of 0
+                    const uint32_t src_bytes = (x_fixed + 4 * lane < (int)ld_t) ? 16u : 0u;
+                    const float* src0 = g.table + (src_bytes ? x_fixed + 4 * lane : 0);
+                    int ids[kChunk];
+#pragma unroll
+                    for (int i = 0; i < kChunk; ++i) ids[i] = __shfl_sync(0xffffffffu, my_id, i);
+#pragma unroll
+                    for (int i = 0; i < kChunk; ++i)
+                        cp_async16(st + (uint32_t)(i * (kTile * 4) + lane * 16), src0 + (int64_t)ids[i] * ld_t, src_bytes);
+                    cp_async_arrive(full);
+                }
             }
+            TC_TRACE(1, c);
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
         // The whole warp runs the loop (waits are warp-uniform); one elected lane issues.  Descriptors
         // are base + small offset so that each tcgen05.mma costs a couple of uniform-datapath adds.
         constexpr uint32_t idesc = make_idesc(TN);
-        const uint64_t yh_base = TN ? make_desc(base + kOperandBytes, 4096, 512, 1u) : make_desc(base + kOperandBytes, 16, 1024);
+        const uint64_t yh_base = TN ? make_desc(base + kXBytes, 4096, 512, 1u) : make_desc(base + kXBytes, 16, 1024);
         const uint32_t d_corr = tmem + (uint32_t)kMainAccs * kTile;
         const bool leader = elect_one();
         for (int c = 0; c < nchunks; ++c) {
@@ -342,7 +427,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < 16; ++k) { hi[k] = 0; lo[k] = 0; }
                 } else if (!TN) {
-                    // row `row` of the SWIZZLE_128B tile: 16-B chunk j sits at position j ^ (row % 8)
+                    // row `row` of the SWIZZLE_128B tile (TMA-written or gathered): 16-B chunk j sits at position j ^ (row % 8)
                     const float4* xr = reinterpret_cast<const float4*>(xs + row * 128);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -415,11 +500,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     }
                 }
             } else {
-                // thread = column (x_fixed + row) of X, registers = 16 d_out rows of dW: transposed store,
-                // consecutive lanes write consecutive columns -> one 128-B line per d_out row per warp
+                // thread = column (x_fixed + row) of its half of X, registers = 16 d_out rows of dW: transposed
+                // store, consecutive lanes write consecutive columns -> one 128-B line per d_out row per warp
                 const int col = x_fixed + row;
-                if (col < g.k_in) {
-                    float* dst = g.out + (int64_t)blockIdx.y * g.split_stride + (int64_t)(cb * 16) * g.ld_out + col;
+                if (col < col_limit) {
+                    float* dst = g.out + (int64_t)blockIdx.y * g.split_stride + (int64_t)(cb * 16) * g.ld_out + out_col0 + col;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) dst[(int64_t)i * g.ld_out] = __uint_as_float(r[i]);
                 }
@@ -513,12 +598,11 @@ int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64
     return r == CUDA_SUCCESS ? GS_OK : GS_EINVAL;
 }
 
-int tn_splits(int n_max, int k_in) {
+int tn_splits(int n_max, int tiles) {
     // Enough splits that (a) no CTA accumulates more than kMaxChunksPerSplit stages (bounds the
     // round-toward-zero accumulation bias, see kMainAccs) and (b) tiles x splits fills whole
     // waves of 148 CTAs (1 CTA/SM): the split count is rounded up to the end of the last wave.
     constexpr int kMaxChunksPerSplit = 32;
-    const int tiles = (k_in + kTile - 1) / kTile;
     int need = (n_max + kMaxChunksPerSplit * kChunk - 1) / (kMaxChunksPerSplit * kChunk);
     if (need < 1) need = 1;
     const int waves = (tiles * need + GS_NUM_SMS - 1) / GS_NUM_SMS;
@@ -527,6 +611,19 @@ int tn_splits(int n_max, int k_in) {
     const int cap = (n_max + 4 * kChunk - 1) / (4 * kChunk);       // at least 4 stages of work per CTA
     if (s > cap) s = cap;
     return s < 1 ? 1 : s;
+}
+
+// experiment switches: read once per process, zero / null in production
+int tc_debug() {
+    static int v = -1;
+    if (v < 0) v = getenv("GSAGE_TC_DEBUG") ? atoi(getenv("GSAGE_TC_DEBUG")) : 0;
+    return v;
+}
+int tc_prefetch() {
+    return getenv("GSAGE_TC_PREFETCH") ? atoi(getenv("GSAGE_TC_PREFETCH")) : 0;
+}
+long long* tc_trace() {
+    return getenv("GSAGE_TC_TRACE") ? (long long*)strtoull(getenv("GSAGE_TC_TRACE"), nullptr, 10) : nullptr;
 }
 
 int grid1d(int64_t total) {
@@ -543,9 +640,111 @@ extern "C" int gs_encoder_tc_supported(int32_t k_in, int32_t d_out) {
     return (d_out == kTile && k_in >= kChunk) ? 1 : 0;
 }
 
-// floats of workspace for the forward: W_hi + W_lo
+namespace {
+
+inline int64_t round4(int64_t v) { return (v + 3) & ~(int64_t)3; }
+
+// Where X comes from: one dense matrix, or [table[self_ids] | dense] with the self half gathered in the kernel.
+struct XSource {
+    const float* x; int64_t ld_x; int32_t k_dense;             // dense part (the whole X, or the mean half)
+    const float* table; int64_t ld_table; const int32_t* self_ids; int32_t self_cols;   // table == nullptr: no self half
+};
+
+int check_xsource(const XSource& xs) {
+    if (!xs.x || xs.k_dense <= 0) return GS_EINVAL;
+    if (!gs_aligned16(xs.x) || (xs.ld_x & 3) || xs.ld_x < xs.k_dense) return GS_EALIGN;
+    if (xs.table) {
+        if (!xs.self_ids || xs.self_cols <= 0 || xs.ld_table < xs.self_cols) return GS_EINVAL;
+        if (!gs_aligned16(xs.table) || (xs.ld_table & 3)) return GS_EALIGN;
+    }
+    return GS_OK;
+}
+
+// W [d_out, self_cols + k_dense] -> W_hi / W_lo in ws, each [d_out, ldw] with the self columns at [0, self_cols) and the
+// dense columns at [round4(self_cols), ...): both halves start 16-B aligned, which their TMA maps need
+int launch_fwd(const XSource& xs, const float* w, int64_t ld_w, int32_t d_out, int32_t act, int32_t n_max,
+               const int32_t* n_dev, float* h, int64_t ld_h, float* ws, cudaStream_t s) {
+    const int32_t sc = xs.table ? xs.self_cols : 0;
+    const int64_t off = round4(sc), ldw = off + round4(xs.k_dense);
+    float* w_hi = ws;
+    float* w_lo = ws + (int64_t)d_out * ldw;
+    GS_PREFER_SMEM(split_rows_kernel);
+    if (sc) {
+        split_rows_kernel<<<grid1d((int64_t)d_out * sc), 256, 0, s>>>(w, ld_w, d_out, sc, w_hi, w_lo, ldw);
+        GS_LAUNCH_CHECK();
+    }
+    split_rows_kernel<<<grid1d((int64_t)d_out * xs.k_dense), 256, 0, s>>>(w + sc, ld_w, d_out, xs.k_dense, w_hi + off,
+                                                                          w_lo + off, ldw);
+    GS_LAUNCH_CHECK();
+    CUtensorMap mx, mh, ml, msh, msl;
+    int rc;
+    if ((rc = make_map(&mx, xs.x, n_max, xs.k_dense, xs.ld_x, kChunk, kTile))) return rc;
+    if ((rc = make_map(&mh, w_hi + off, d_out, xs.k_dense, ldw, kChunk, kTile))) return rc;
+    if ((rc = make_map(&ml, w_lo + off, d_out, xs.k_dense, ldw, kChunk, kTile))) return rc;
+    msh = mh; msl = ml;
+    if (sc) {
+        if ((rc = make_map(&msh, w_hi, d_out, sc, ldw, kChunk, kTile))) return rc;
+        if ((rc = make_map(&msl, w_lo, d_out, sc, ldw, kChunk, kTile))) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    TcArgs g{n_max, n_dev, xs.k_dense, act, h, ld_h, 0, 0, xs.table, xs.ld_table, xs.self_ids,
+             sc ? (sc + kChunk - 1) / kChunk : 0, sc, tc_prefetch(), tc_debug(), tc_trace()};
+    tc_gemm_kernel<false><<<(n_max + kTile - 1) / kTile, kThreads, kSmemBytes, s>>>(mx, mh, ml, msh, msl, g);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+int launch_wgrad(const XSource& xs, const float* h, int64_t ld_h, const float* gh, int64_t ld_gh, int32_t d_out,
+                 int32_t act, int32_t n_max, const int32_t* n_dev, float* gw, int64_t ld_gw, float* ws, cudaStream_t s) {
+    const int32_t sc = xs.table ? xs.self_cols : 0;
+    const int32_t k_all = sc + xs.k_dense;
+    const int64_t ldw = round4(k_all);
+    float* dz_hi = ws;
+    float* dz_lo = ws + (int64_t)n_max * d_out;
+    float* part = ws + 2 * (int64_t)n_max * d_out;
+    GS_PREFER_SMEM(act_grad_rows_kernel);
+    GS_PREFER_SMEM(tc_reduce_kernel);
+    act_grad_rows_kernel<<<grid1d((int64_t)n_max * (d_out / 4)), 256, 0, s>>>(h, ld_h, gh, ld_gh, d_out, act, n_max, n_dev,
+                                                                             dz_hi, dz_lo);
+    GS_LAUNCH_CHECK();
+    const int self_tiles = sc ? (sc + kTile - 1) / kTile : 0;
+    const int tiles = self_tiles + (xs.k_dense + kTile - 1) / kTile;
+    const int splits = tn_splits(n_max, tiles);
+    int rps = (n_max + splits - 1) / splits;
+    rps = ((rps + kChunk - 1) / kChunk) * kChunk;
+    CUtensorMap mx, mh, ml;
+    int rc;
+    const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;    // MN-major tf32 operand layout
+    if ((rc = make_map(&mx, xs.x, n_max, xs.k_dense, xs.ld_x, kTile, kChunk, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+    if ((rc = make_map(&mh, dz_hi, n_max, d_out, d_out, 32, kChunk, swz))) return rc;
+    if ((rc = make_map(&ml, dz_lo, n_max, d_out, d_out, 32, kChunk, swz))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    TcArgs g{n_max, n_dev, xs.k_dense, GS_ACT_NONE, part, ldw, rps, (int64_t)d_out * ldw, xs.table, xs.ld_table, xs.self_ids,
+             self_tiles, sc, tc_prefetch(), tc_debug(), nullptr};
+    dim3 grid(tiles, splits);
+    tc_gemm_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(mx, mh, ml, mh, ml, g);
+    GS_LAUNCH_CHECK();
+    tc_reduce_kernel<<<grid1d((int64_t)d_out * k_all), 256, 0, s>>>(part, splits, (int64_t)d_out * ldw, ldw, d_out, k_all,
+                                                                   gw, ld_gw);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+}  // namespace
+
+// floats of workspace for the forward: W_hi + W_lo (k_in = all columns of W; room for the 16-B aligned start of a second half)
 extern "C" int64_t gs_encoder_fwd_tc_ws_floats(int32_t k_in, int32_t d_out) {
-    return 2 * (int64_t)d_out * ((k_in + 3) & ~3);      // W_hi + W_lo
+    return 2 * (int64_t)d_out * (round4(k_in) + 4);
 }
 
 extern "C" int gs_encoder_fwd_tc(const float* x, int64_t ld_x, const float* w, int64_t ld_w,
@@ -557,35 +756,34 @@ extern "C" int gs_encoder_fwd_tc(const float* x, int64_t ld_x, const float* w, i
     if (!gs_aligned16(x) || !gs_aligned16(w) || !gs_aligned16(h) || !gs_aligned16(ws) || (ld_x & 3) || (ld_w & 3) || (ld_h & 3))
         return GS_EALIGN;
     if (n_max == 0) return GS_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    const int64_t ldw = (k_in + 3) & ~3;
-    float* w_hi = ws;
-    float* w_lo = ws + (int64_t)d_out * ldw;
-    GS_PREFER_SMEM(split_rows_kernel);
-    split_rows_kernel<<<grid1d((int64_t)d_out * k_in), 256, 0, s>>>(w, ld_w, d_out, k_in, w_hi, w_lo, ldw);
-    GS_LAUNCH_CHECK();
-    CUtensorMap mx, mh, ml;
-    int rc;
-    if ((rc = make_map(&mx, x, n_max, k_in, ld_x, kChunk, kTile))) return rc;
-    if ((rc = make_map(&mh, w_hi, d_out, k_in, ldw, kChunk, kTile))) return rc;
-    if ((rc = make_map(&ml, w_lo, d_out, k_in, ldw, kChunk, kTile))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    TcArgs g{n_max, n_dev, k_in, act, h, ld_h, 0, 0, getenv("GSAGE_TC_DEBUG") ? atoi(getenv("GSAGE_TC_DEBUG")) : 0,
-             getenv("GSAGE_TC_TRACE") ? (long long*)strtoull(getenv("GSAGE_TC_TRACE"), nullptr, 10) : nullptr};
-    tc_gemm_kernel<false><<<(n_max + kTile - 1) / kTile, kThreads, kSmemBytes, s>>>(mx, mh, ml, g);
-    GS_LAUNCH_CHECK();
-    return GS_OK;
+    return launch_fwd(XSource{x, ld_x, k_in, nullptr, 0, nullptr, 0}, w, ld_w, d_out, act, n_max, n_dev, h, ld_h, ws,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int gs_sage_encoder_fwd_tc(const float* table, int64_t ld_table, const int32_t* self_ids, int32_t feat_dim,
+                                      const float* mean, int64_t ld_mean, const float* w, int64_t ld_w,
+                                      int32_t d_out, int32_t act, int32_t n_max, const int32_t* n_dev,
+                                      float* h, int64_t ld_h, float* ws, void* stream) {
+    if (!table || !self_ids || !mean || !w || !h || !ws || n_max < 0 || feat_dim <= 0) return GS_EINVAL;
+    if (!gs_encoder_tc_supported(feat_dim, d_out)) return GS_ENOSUP;
+    XSource xs{mean, ld_mean, feat_dim, table, ld_table, self_ids, feat_dim};
+    int rc = check_xsource(xs);
+    if (rc) return rc;
+    if (!gs_aligned16(w) || !gs_aligned16(h) || !gs_aligned16(ws) || (ld_w & 3) || (ld_h & 3)) return GS_EALIGN;
+    if (ld_w < 2 * (int64_t)feat_dim) return GS_EINVAL;
+    if (n_max == 0) return GS_OK;
+    return launch_fwd(xs, w, ld_w, d_out, act, n_max, n_dev, h, ld_h, ws, (cudaStream_t)stream);
 }
 
 // floats of workspace for the weight gradient: dz_hi + dz_lo + split-K partials
 extern "C" int64_t gs_encoder_wgrad_tc_ws_floats(int32_t n_max, int32_t k_in, int32_t d_out) {
-    const int64_t ldw = (k_in + 3) & ~3;
-    return 2 * (int64_t)(n_max > 0 ? n_max : 1) * d_out + (int64_t)tn_splits(n_max, k_in) * d_out * ldw;
+    const int64_t ldw = round4(k_in);
+    // one column tile more than ceil(k_in / 128): a SAGE call tiles its two halves separately
+    const int tiles = (k_in + kTile - 1) / kTile + 1;
+    int splits = tn_splits(n_max, tiles);
+    const int s2 = tn_splits(n_max, tiles - 1);
+    if (s2 > splits) splits = s2;
+    return 2 * (int64_t)(n_max > 0 ? n_max : 1) * d_out + (int64_t)splits * d_out * ldw;
 }
 
 extern "C" int gs_encoder_wgrad_tc(const float* x, int64_t ld_x, const float* h, int64_t ld_h,
@@ -597,37 +795,22 @@ extern "C" int gs_encoder_wgrad_tc(const float* x, int64_t ld_x, const float* h,
     if (!gs_aligned16(x) || !gs_aligned16(ws) || !gs_aligned16(h) || !gs_aligned16(gh) || (ld_x & 3) || (ld_h & 3) || (ld_gh & 3))
         return GS_EALIGN;
     if (n_max == 0) return GS_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    const int64_t ldw = (k_in + 3) & ~3;
-    float* dz_hi = ws;
-    float* dz_lo = ws + (int64_t)n_max * d_out;
-    float* part = ws + 2 * (int64_t)n_max * d_out;
-    GS_PREFER_SMEM(act_grad_rows_kernel);
-    GS_PREFER_SMEM(tc_reduce_kernel);
-    act_grad_rows_kernel<<<grid1d((int64_t)n_max * (d_out / 4)), 256, 0, s>>>(h, ld_h, gh, ld_gh, d_out, act, n_max, n_dev,
-                                                                             dz_hi, dz_lo);
-    GS_LAUNCH_CHECK();
-    const int splits = tn_splits(n_max, k_in);
-    int rps = (n_max + splits - 1) / splits;
-    rps = ((rps + kChunk - 1) / kChunk) * kChunk;
-    CUtensorMap mx, mh, ml;
-    int rc;
-    const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;    // MN-major tf32 operand layout
-    if ((rc = make_map(&mx, x, n_max, k_in, ld_x, kTile, kChunk, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
-    if ((rc = make_map(&mh, dz_hi, n_max, d_out, d_out, 32, kChunk, swz))) return rc;
-    if ((rc = make_map(&ml, dz_lo, n_max, d_out, d_out, 32, kChunk, swz))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    TcArgs g{n_max, n_dev, k_in, GS_ACT_NONE, part, ldw, rps, (int64_t)d_out * ldw, getenv("GSAGE_TC_DEBUG") ? atoi(getenv("GSAGE_TC_DEBUG")) : 0, nullptr};
-    dim3 grid((k_in + kTile - 1) / kTile, splits);
-    tc_gemm_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(mx, mh, ml, g);
-    GS_LAUNCH_CHECK();
-    tc_reduce_kernel<<<grid1d((int64_t)d_out * k_in), 256, 0, s>>>(part, splits, (int64_t)d_out * ldw, ldw, d_out, k_in,
-                                                                  gw, ld_gw);
-    GS_LAUNCH_CHECK();
-    return GS_OK;
+    return launch_wgrad(XSource{x, ld_x, k_in, nullptr, 0, nullptr, 0}, h, ld_h, gh, ld_gh, d_out, act, n_max, n_dev, gw,
+                        ld_gw, ws, (cudaStream_t)stream);
+}
+
+extern "C" int gs_sage_encoder_wgrad_tc(const float* table, int64_t ld_table, const int32_t* self_ids, int32_t feat_dim,
+                                        const float* mean, int64_t ld_mean, const float* h, int64_t ld_h,
+                                        const float* gh, int64_t ld_gh, int32_t d_out, int32_t act,
+                                        int32_t n_max, const int32_t* n_dev, float* gw, int64_t ld_gw, float* ws,
+                                        void* stream) {
+    if (!table || !self_ids || !mean || !h || !gh || !gw || !ws || n_max < 0 || feat_dim <= 0) return GS_EINVAL;
+    if (!gs_encoder_tc_supported(feat_dim, d_out)) return GS_ENOSUP;
+    XSource xs{mean, ld_mean, feat_dim, table, ld_table, self_ids, feat_dim};
+    int rc = check_xsource(xs);
+    if (rc) return rc;
+    if (!gs_aligned16(ws) || !gs_aligned16(h) || !gs_aligned16(gh) || (ld_h & 3) || (ld_gh & 3)) return GS_EALIGN;
+    if (ld_gw < 2 * (int64_t)feat_dim) return GS_EINVAL;
+    if (n_max == 0) return GS_OK;
+    return launch_wgrad(xs, h, ld_h, gh, ld_gh, d_out, act, n_max, n_dev, gw, ld_gw, ws, (cudaStream_t)stream);
 }

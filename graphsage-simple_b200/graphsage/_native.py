@@ -36,6 +36,10 @@ SIGNATURES = {
     "gs_encoder_wgrad_tc_ws_floats": (_i64, [_i32, _i32, _i32]),
     "gs_encoder_wgrad_tc": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr,
                                    _ptr, _i64, _ptr, _ptr]),
+    "gs_sage_encoder_fwd_tc": (_i32, [_ptr, _i64, _ptr, _i32, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _ptr,
+                                      _ptr, _i64, _ptr, _ptr]),
+    "gs_sage_encoder_wgrad_tc": (_i32, [_ptr, _i64, _ptr, _i32, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _i32,
+                                        _i32, _ptr, _ptr, _i64, _ptr, _ptr]),
     "gs_classifier_ws_floats": (_i64, [_i32, _i32, _i32]),
     "gs_classifier_xent": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i32, _i32, _i32, _f32, _ptr, _i64, _ptr,
                                   _ptr, _i64, _ptr, _i64, _ptr, _ptr]),

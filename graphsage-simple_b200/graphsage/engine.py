@@ -45,7 +45,9 @@ class _FrontierSet:
         self.n1_dev = torch.zeros(1, **i32)
         self.idx1 = torch.empty((n1_max, eng.w1_width), **i32)
         self.cnt1 = torch.empty(n1_max, **i32)
-        self.comb1 = ops.empty_rows(n1_max, eng.K1, dev, zero=True)
+        # SAGE on the tensor-core path: only the neighbour-mean half [n1, F] exists; the self half of the combined
+        # tile is gathered from the feature table inside the GEMMs (gs_sage_encoder_*_tc)
+        self.comb1 = ops.empty_rows(n1_max, eng.F if eng.split_self else eng.K1, dev, zero=True)
 
 
 class TrainEngine:
@@ -76,6 +78,16 @@ class TrainEngine:
         self.n1_max = n1_max
         self.K1 = self.F if self.gcn else 2 * self.F
         self.K2 = self.d1 if self.gcn else 2 * self.d1
+        # layer 1 runs on the tcgen05 path when the shape qualifies (d1 == 128, K1 >= 32)
+        self.tc1 = ops.encoder_tc_supported(self.K1, self.d1)
+        # ... and, in SAGE mode on a local table, can consume the concat in place ([table[v] | mean] never written:
+        # gs_sage_encoder_*_tc).  Measured on B200 (profiles/README.md, round 2): -122 MB of HBM traffic per step and a
+        # 25 % shorter gather, but the GEMMs' single producer warp cannot issue the 32 row-gather copies per chunk fast
+        # enough (forward 86 vs 72 us, weight gradient 104 vs 71 us) and the step gets SLOWER (0.268 vs 0.241 ms), so
+        # it is opt-in (GSAGE_SPLIT_SELF=1), parity-tested either way.
+        self.split_self = (self.tc1 and not self.gcn and self.table_peer is None and
+                           ops.encoder_tc_supported(self.F, self.d1) and
+                           bool(int(__import__('os').environ.get('GSAGE_SPLIT_SELF', '0'))))
         self.sets = [_FrontierSet(self)]           # sets 2 and 3 are created on first pipelined use
         self.cur = 0
         self.loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -97,8 +109,6 @@ class TrainEngine:
                  ops.encoder_bwd_ws_floats(B, self.K2, self.d2), 4)
         self.ws = torch.empty(ws, device=dev)
         self.xent_ws = torch.empty(ops.classifier_ws_floats(B, self.d2, self.C), device=dev)
-        # layer 1 runs on the tcgen05 path when the shape qualifies (d1 == 128, K1 % 4 == 0)
-        self.tc1 = ops.encoder_tc_supported(self.K1, self.d1)
         self.tc2 = ops.encoder_tc_supported(self.K2, self.d2) and B >= 512
         need = [4]
         if self.tc1:
@@ -189,7 +199,8 @@ class TrainEngine:
     def _gather(self, fs, b):
         """Stage 2: the HBM-bound (partitioned: NVLink-bound) layer-1 gather-mean over the sampled tile -> comb1."""
         n1_max = self._n1_max(b)
-        kw = dict(neigh_off=0 if self.gcn else self.F, self_ids=None if self.gcn else fs.frontier1[:n1_max],
+        plain = self.gcn or self.split_self                # no self half in the tile this kernel writes
+        kw = dict(neigh_off=0 if plain else self.F, self_ids=None if plain else fs.frontier1[:n1_max],
                   n_dev=fs.n1_dev)
         if self.table_peer is not None:
             tp = self.table_peer
@@ -213,7 +224,10 @@ class TrainEngine:
             self._aux.wait_stream(main)
             with torch.cuda.stream(self._aux):
                 gh1.zero_()
-        if self.tc1:
+        if self.split_self:
+            ops.sage_encoder_fwd_tc(self.table, fs.frontier1[:n1_max], self.F, comb1, self.w1, self.act1, h1,
+                                    ws=self.tc_ws, n_dev=fs.n1_dev)
+        elif self.tc1:
             ops.encoder_fwd_tc(comb1, self.w1, self.act1, h1, ws=self.tc_ws, n_dev=fs.n1_dev)
         else:
             ops.encoder_fwd(comb1, self.w1, self.act1, h1, n_dev=fs.n1_dev)
@@ -249,7 +263,10 @@ class TrainEngine:
         self._wgrad1(fs, comb1, h1, gh1)
 
     def _wgrad1(self, fs, comb1, h1, gh1):
-        if self.tc1:
+        if self.split_self:
+            ops.sage_encoder_wgrad_tc(self.table, fs.frontier1[:comb1.shape[0]], self.F, comb1, h1, gh1, self.act1,
+                                      self.gw1, ws=self.tc_ws, n_dev=fs.n1_dev)
+        elif self.tc1:
             ops.encoder_wgrad_tc(comb1, h1, gh1, self.act1, self.gw1, ws=self.tc_ws, n_dev=fs.n1_dev)
         else:
             ops.encoder_bwd(comb1, self.w1, h1, gh1, self.act1, self.gw1, None, dz=self.dz1, ws=self.ws,

@@ -218,6 +218,36 @@ def encoder_wgrad_tc(x, h, gh, act, gw, ws=None, n_dev=None):
     return gw
 
 
+def sage_encoder_fwd_tc(table, self_ids, feat_dim, mean, w, act, h, ws=None, n_dev=None):
+    """h = act([table[self_ids] | mean] . w^T) on tcgen05; the self rows are gathered from the table inside the
+    GEMM's producer (the self half of the combined tile is never materialised) -- see gs_sage_encoder_fwd_tc."""
+    lib = N.load()
+    N.require_cuda(table, self_ids, mean, w, h)
+    n_max, d_out = mean.shape[0], w.shape[0]
+    if ws is None:
+        ws = torch.empty(encoder_fwd_tc_ws_floats(2 * feat_dim, d_out), device=mean.device, dtype=torch.float32)
+    N.check(lib.gs_sage_encoder_fwd_tc(N.ptr(table), table.stride(0), N.ptr(self_ids), int(feat_dim), N.ptr(mean),
+                                       mean.stride(0), N.ptr(w), w.stride(0), d_out, int(act), n_max, N.ptr(n_dev),
+                                       N.ptr(h), h.stride(0), N.ptr(ws), N.stream()), "gs_sage_encoder_fwd_tc")
+    LAUNCHES[0] += 3
+    return h
+
+
+def sage_encoder_wgrad_tc(table, self_ids, feat_dim, mean, h, gh, act, gw, ws=None, n_dev=None):
+    """gw [d_out, 2 F] = (gh * act'(h))^T . [table[self_ids] | mean] on tcgen05 -- see gs_sage_encoder_wgrad_tc."""
+    lib = N.load()
+    N.require_cuda(table, self_ids, mean, h, gh, gw)
+    n_max, d_out = mean.shape[0], h.shape[1]
+    if ws is None:
+        ws = torch.empty(encoder_wgrad_tc_ws_floats(n_max, 2 * feat_dim, d_out), device=mean.device, dtype=torch.float32)
+    N.check(lib.gs_sage_encoder_wgrad_tc(N.ptr(table), table.stride(0), N.ptr(self_ids), int(feat_dim), N.ptr(mean),
+                                         mean.stride(0), N.ptr(h), h.stride(0), N.ptr(gh), gh.stride(0), d_out,
+                                         int(act), n_max, N.ptr(n_dev), N.ptr(gw), gw.stride(0), N.ptr(ws), N.stream()),
+            "gs_sage_encoder_wgrad_tc")
+    LAUNCHES[0] += 3
+    return gw
+
+
 def classifier_ws_floats(n, d, c):
     return int(N.load().gs_classifier_ws_floats(int(n), int(d), int(c)))
 

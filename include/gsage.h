@@ -151,7 +151,7 @@ GS_API int gs_encoder_dgrad(const float* w, int64_t ld_w, const float* h, int64_
 
 /* ---- K3 on tcgen05 tensor cores (3xTF32, fp32 accumulation in TMEM) ------------------------
  * Same contracts as gs_encoder_fwd and the gw part of gs_encoder_bwd, for the shapes
- * gs_encoder_tc_supported() accepts (d_out == 128, k_in % 4 == 0).  The three-term hi/lo
+ * gs_encoder_tc_supported() accepts (d_out == 128, k_in >= 32).  The three-term hi/lo
  * TF32 split keeps results within 1e-5 (norm-wise) of the fp32 reference path.
  * ws: gs_encoder_fwd_tc_ws_floats / gs_encoder_wgrad_tc_ws_floats floats, 16-B aligned.    */
 GS_API int gs_encoder_tc_supported(int32_t k_in, int32_t d_out);
@@ -160,6 +160,21 @@ GS_API int gs_encoder_fwd_tc(const float* x, int64_t ld_x, const float* w, int64
                       int32_t k_in, int32_t d_out, int32_t act,
                       int32_t n_max, const int32_t* n_dev,
                       float* h, int64_t ld_h, float* ws, void* stream);
+/* SAGE concat consumed in place (encoders.py:49-61 as ONE op for the rows of the feature table):
+ *   h = act([table[self_ids] | mean] . w^T)          w [d_out, 2 * feat_dim] = [W_self | W_neigh]
+ * `mean` [n, feat_dim] is the neighbour mean gs_gather_mean_fwd wrote (self_ids == NULL, neigh_off == 0); the self
+ * half of the combined tile is NOT materialised: the GEMM's producer warp gathers the rows `self.features(nodes)`
+ * (encoders.py:53) straight from the table into its shared-memory stage ring, and the tcgen05 MMAs consume them
+ * there.  gs_sage_encoder_wgrad_tc is the matching weight gradient gw [d_out, 2 * feat_dim] = dz^T . [table[self_ids] | mean].
+ * ws sizes: gs_encoder_fwd_tc_ws_floats(2 * feat_dim, d_out), gs_encoder_wgrad_tc_ws_floats(n_max, 2 * feat_dim, d_out). */
+GS_API int gs_sage_encoder_fwd_tc(const float* table, int64_t ld_table, const int32_t* self_ids, int32_t feat_dim,
+                           const float* mean, int64_t ld_mean, const float* w, int64_t ld_w,
+                           int32_t d_out, int32_t act, int32_t n_max, const int32_t* n_dev,
+                           float* h, int64_t ld_h, float* ws, void* stream);
+GS_API int gs_sage_encoder_wgrad_tc(const float* table, int64_t ld_table, const int32_t* self_ids, int32_t feat_dim,
+                             const float* mean, int64_t ld_mean, const float* h, int64_t ld_h,
+                             const float* gh, int64_t ld_gh, int32_t d_out, int32_t act,
+                             int32_t n_max, const int32_t* n_dev, float* gw, int64_t ld_gw, float* ws, void* stream);
 GS_API int64_t gs_encoder_wgrad_tc_ws_floats(int32_t n_max, int32_t k_in, int32_t d_out);
 GS_API int gs_encoder_wgrad_tc(const float* x, int64_t ld_x, const float* h, int64_t ld_h,
                         const float* gh, int64_t ld_gh, int32_t k_in, int32_t d_out, int32_t act,

@@ -65,3 +65,19 @@ def test_fused_train_step_matches_reference_at_baseline_widths(golden, name):
     assert relerr(enc1.weight.detach().cpu().numpy()[::8, cols], g["w1_new"]) < REL
     scores = model.forward(list(x["nodes"]))          # op-by-op forward with the updated weights stays finite / shaped
     assert tuple(scores.shape) == g["scores"].shape and torch.isfinite(scores).all()
+
+
+@pytest.mark.parametrize("name", ["bs_reddit", "bs_pubmed"])
+def test_in_place_concat_variant_matches_reference(golden, name, monkeypatch):
+    """GSAGE_SPLIT_SELF=1: the engine keeps only the neighbour-mean half of the layer-1 tile and the tcgen05 GEMMs
+    gather the self rows from the feature table in their producer warp (gs_sage_encoder_fwd_tc / _wgrad_tc,
+    encoders.py:53-61 as one op).  Same reference outputs."""
+    monkeypatch.setenv("GSAGE_SPLIT_SELF", "1")
+    g, p, x, model, enc1, enc2 = _model(name, golden)
+    loss = model.train_step(list(x["nodes"]), x["labels"][x["nodes"]], lr=0.7)
+    eng = model._engine
+    assert eng.split_self and eng.sets[0].comb1.shape[1] == p["f"]          # only the mean half exists
+    assert abs(loss - float(g["loss"])) / abs(float(g["loss"])) < REL
+    assert relerr(eng.gw1.cpu().numpy(), g["gw1"]) < REL
+    assert relerr(enc2.weight.detach().cpu().numpy(), g["w2_new"]) < REL
+    assert relerr(enc1.weight.detach().cpu().numpy()[::8], g["w1_new"]) < REL

@@ -290,6 +290,45 @@ def test_encoder_tensor_core_path(ops, n, k_in, act):
     assert relerr(gw.cpu().numpy(), (dz.t() @ x.double()).cpu().numpy()) < REL
 
 
+@pytest.mark.parametrize("n,feat,act,use_n_dev", [(3000, 602, 1, False), (700, 50, 2, True), (129, 128, 1, False),
+                                                  (26000, 602, 1, True), (40, 500, 1, False)])
+def test_sage_encoder_tensor_core_gathers_self_rows_in_place(ops, n, feat, act, use_n_dev):
+    """gs_sage_encoder_fwd_tc / _wgrad_tc: X = [table[self_ids] | mean] with the self half gathered from the feature
+    table inside the GEMM (never materialised), against fp64 and against the plain tcgen05 path fed the concatenated
+    tile (encoders.py:53-61 and its MmBackward)."""
+    g = torch.Generator(device="cuda").manual_seed(n + feat)
+    num_nodes, d = 5000, 128
+    table = ops.empty_rows(num_nodes, feat, "cuda", zero=True)
+    table.copy_(torch.randn(num_nodes, feat, device="cuda", generator=g))
+    n_alloc = n + 300 if use_n_dev else n
+    ids = torch.randint(0, num_nodes, (n_alloc,), device="cuda", generator=g, dtype=torch.int32)
+    ids[:3] = torch.tensor([0, num_nodes - 1, 0], dtype=torch.int32)             # first / last table row, a repeat
+    mean = ops.empty_rows(n_alloc, feat, "cuda", zero=True)
+    mean.copy_(torch.randn(n_alloc, feat, device="cuda", generator=g))
+    w = torch.randn(d, 2 * feat, device="cuda", generator=g) / (2 * feat) ** 0.5
+    gh = torch.randn(n_alloc, d, device="cuda", generator=g)
+    n_dev = torch.tensor([n], dtype=torch.int32, device="cuda") if use_n_dev else None
+    h = torch.full((n_alloc, d), 7.0, device="cuda")
+    ops.sage_encoder_fwd_tc(table, ids, feat, mean, w, act, h, n_dev=n_dev)
+    x = torch.cat([table[ids[:n].long()], mean[:n]], dim=1).double()
+    z = x @ w.double().t()
+    ref = torch.relu(z) if act == 1 else torch.sigmoid(z)
+    assert relerr(h[:n].cpu().numpy(), ref.cpu().numpy()) < REL
+    if use_n_dev:
+        assert (h[(n + 127) // 128 * 128:] == 7.0).all()
+    gw = torch.full((d, 2 * feat), float("nan"), device="cuda")
+    ops.sage_encoder_wgrad_tc(table, ids, feat, mean, h, gh, act, gw, n_dev=n_dev)
+    hd = h[:n].double()
+    dz = gh[:n].double() * ((hd > 0).double() if act == 1 else hd * (1 - hd))
+    assert relerr(gw.cpu().numpy(), (dz.t() @ x).cpu().numpy()) < REL
+    # same numbers as the plain kernels on the materialised tile, up to the summation order of the K chunks
+    comb = ops.empty_rows(n, 2 * feat, "cuda", zero=True)
+    comb.copy_(x.float())
+    h2 = torch.empty((n, d), device="cuda")
+    ops.encoder_fwd_tc(comb, w, act, h2)
+    assert relerr(h2.cpu().numpy(), h[:n].cpu().numpy()) < REL
+
+
 def test_encoder_tensor_core_device_row_count(ops):
     n_max, n, k_in, d_out = 900, 517, 256, 128
     g = torch.Generator(device="cuda").manual_seed(5)
