@@ -221,6 +221,9 @@ int launch_gather_mean(const TableRef& table, bool peer, int64_t ld_table, int32
     // (320 threads x 72 regs = 23 K) or the fused head (256 x 96 = 24.6 K) AND a sampler block (8 K):
     // 3 blocks of 4 warps x 80 regs = 30.7 K, i.e. 12 warps x 10 independent 128-bit loads per lane
     // = 61 KB in flight per SM (Little: 6.5 TB/s x ~800 ns / 148 SMs = 35 KB).  Tunable for experiments.
+    // (Round 2: a column-split variant -- 2 warps per row, 3 chunks x 3 neighbours per lane in 64 registers, 16 warps
+    // per SM = 72 KB in flight -- measured the SAME 0.183 ms: with the 164 KB shared / 64 KB L1 split the co-resident
+    // GEMM needs, the bound is the L1's outstanding-request capacity, not warps x registers; profiles/README.md.)
     static int bps = 0, wpb = 0, carve = 0;
     if (bps == 0) {
         // L1/shared split preference (percent of shared; 1 = max shared, 0 = driver default).  The split can only
