@@ -165,6 +165,45 @@ def cpu_reference_rate(args, rowptr, col, table, labels, w1, w2, wc, batch, step
                                       "%.3f s/step, %d torch threads" % (what, batch, warmup, steps, med, cores))
 
 
+def cpu_reference_rate_stack(rowptr, col, table, labels, feat, hidden, fanouts, classes, lr, batch, steps, warmup=1):
+    """CPU arm of config 5: the UNMODIFIED reference classes stacked three deep by the closure recursion of
+    model.py:220-221 (oracle/ref_runtime.build_stack), or the oracle port (R.StackedModel) when oracle/_ref did not
+    travel, on a bounded batch (the innermost dense mask is batch*16*11 x batch*16*11*6 floats: 0.76 GB at 32)."""
+    import contextlib
+    import random
+    import torch
+    from oracle import ref_path as R
+    from oracle import ref_runtime as RR
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    adj = LazyAdj(rowptr, col)
+    if RR.available() and not os.environ.get("GSAGE_REFERENCE_PORT"):
+        with contextlib.redirect_stdout(sys.stderr):
+            ref = RR.build_stack(table, adj, feat, hidden, fanouts, classes, gcn=False)
+            opt = RR.make_optimizer(ref, lr)
+        step = lambda nodes: RR.train_step(ref, opt, list(nodes), labels[nodes])
+        kind = "reference"
+    else:
+        torch.manual_seed(2)
+        model = R.StackedModel(table, [adj] * len(hidden), hidden, classes, fanouts, gcn=False)
+        step = lambda nodes: model.train_step(list(nodes), labels[nodes], lr=lr)
+        kind = "port"
+    random.seed(2)
+    rng = np.random.default_rng(7)
+    times = []
+    for it in range(warmup + steps):
+        nodes = rng.integers(0, table.shape[0], batch)
+        t0 = time.perf_counter()
+        step(nodes)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    med = float(np.median(times))
+    return batch / med, cores, kind, ("%s, %d layers; bounded sample: B=%d targets/step, %d warm-up + %d timed steps, "
+                                      "median %.3f s/step, %d torch threads" % (
+                                          "unmodified reference classes (oracle/_ref) stacked by closure recursion" if kind == "reference"
+                                          else "oracle port (StackedModel)", len(hidden), batch, warmup, steps, med, cores))
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons through NVML while the timed region runs."""
 
@@ -629,6 +668,10 @@ def build_partitioned_graph(n, pairs, rank, world, seed=2, chunk=1 << 24):
     return rowptr, col
 
 
+def gstep_launches(gstep):
+    return getattr(gstep, "launches_per_step", 0)
+
+
 def run_products(args):
     """BASELINE config 5: synthetic ogbn-products-shape graph, 3-layer SAGE-mean (fan-out 15/10/5 from the
     targets outward), feature table AND CSR partitioned by owner = id % world, every lookup an NCCL
@@ -659,31 +702,44 @@ def run_products(args):
     peer = args.exchange == "peer"
     graph = sharded.ShardedCSR(rowptr, col, n, int(deg_max.item()), ex, dev, peer=peer)
     entries_local = int(col.shape[0])
+    host_csr = (rowptr, col) if (world == 1 and not args.no_cpu_baseline) else None      # N = 1: the CPU baseline's graph
     del rowptr, col
     gen = torch.Generator(device=dev)
     gen.manual_seed(2)
     full = torch.randn(n, feat, device=dev, generator=gen)      # 0.96 GB transient; each rank keeps its rows
     feats = sharded.ShardedFeatures(full[rank::world].contiguous(), n, exchange=ex, peer=peer)
+    host_table = full.cpu() if host_csr is not None else None
     del full
     labels_np = np.random.default_rng(2).integers(0, classes, (n, 1)).astype(np.int64)
     torch.manual_seed(2)
     model, encs = build_sage(feats, feat, [args.hidden] * 3, graph, fan, classes)
     sampling.seed(2)
     build_s = time.perf_counter() - t0
-    opt = torch.optim.SGD(model.parameters(), lr=args.lr)
     rng = np.random.default_rng(200 + rank)
     params = list(model.parameters())
+    graphed = peer and not os.environ.get("GSAGE_PRODUCTS_EAGER")
+    if graphed:
+        # forward + backward (+ SGD on one GPU) of the whole 3-layer step captured as ONE CUDA graph: aggregators in
+        # static-shape mode (no size read back from the device), sampler step in device memory (model.GraphedStep)
+        from graphsage.model import GraphedStep
+        gstep = GraphedStep(model, B, lr=args.lr, world=world, n_global=B * world)
 
-    def step():
-        nodes = rng.integers(0, n, B)
-        opt.zero_grad()
-        loss = model.loss(nodes, labels_np[nodes])
-        loss.backward()
-        sharded.allreduce_grads(params, world, B, B * world)
-        opt.step()
-        return loss
+        def step():
+            nodes = rng.integers(0, n, B)
+            return gstep(nodes, labels_np[nodes])
+    else:
+        opt = torch.optim.SGD(model.parameters(), lr=args.lr)
 
-    for _ in range(W):
+        def step():
+            nodes = rng.integers(0, n, B)
+            opt.zero_grad()
+            loss = model.loss(nodes, labels_np[nodes])
+            loss.backward()
+            sharded.allreduce_grads(params, world, B, B * world)
+            opt.step()
+            return loss
+
+    for _ in range(W + (3 if graphed else 0)):           # graphed: two eager steps, the capture, then replays
         step()
     torch.cuda.synchronize()
     if world > 1:
@@ -709,6 +765,50 @@ def run_products(args):
     ms_total = float(t.item())
     value = world * B * K / (ms_total / 1e3)
     sent = (ex.bytes_sent - sent0) / K
+    # roofline of the partitioned path's dominant kernel: the innermost feature lookup, gs_gather_rows_peer over the
+    # padded hop-3 frontier (B * 16 * 11 * 5 ids of 100 floats), (world-1)/world of whose rows cross NVLink; rank 0's
+    # launch timed alone with CUDA events while the peers idle
+    roof = None
+    if peer:
+        n_rows = min(B * 16 * 11 * 5, n)
+        ids = torch.randint(0, n, (n_rows,), device=dev, dtype=torch.int32)
+        out = torch.empty((n_rows, feats.ld), device=dev)
+        if rank == 0:
+            for _ in range(2):
+                ops.gather_rows_peer(feats.table_ptrs, world, feats.ld, feats.ld, ids, out)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ops.gather_rows_peer(feats.table_ptrs, world, feats.ld, feats.ld, ids, out)
+            e1.record()
+            torch.cuda.synchronize()
+            g_ms = e0.elapsed_time(e1) / 5
+            row_bytes = n_rows * feat * 4
+            if world > 1:
+                remote = row_bytes * (world - 1) / world
+                ach = remote / (g_ms * 1e-3) / 1e9
+                roof = {"kernel": "gather_rows_kernel<PEER> (innermost feature lookup, %d/%d of the rows read from peers over NVLink)" % (world - 1, world),
+                        "bound": "nvlink", "achieved": ach, "peak": 770.0, "unit": "GB/s", "frac": ach / 770.0,
+                        "peak_source": "measured peer-copy bandwidth per direction per GPU (B200_PROFILING.md; 900 nominal)",
+                        "traffic": None, "algorithmic_remote_bytes_per_launch": remote, "rows": n_rows, "avg_launch_ms": g_ms,
+                        "timing": "rank 0's kernel launched alone (eager, CUDA events), peers idle"}
+            else:
+                peak = 6650.0
+                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+                    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+                ach = (row_bytes + n_rows * 4) / (g_ms * 1e-3) / 1e9
+                roof = {"kernel": "gather_rows_kernel (innermost feature lookup, one GPU: all rows local)", "bound": "hbm",
+                        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                        "algorithmic_bytes_per_launch": row_bytes + n_rows * 4, "rows": n_rows, "avg_launch_ms": g_ms,
+                        "timing": "kernel launched alone (eager, CUDA events); rows read once, written once (write not counted)"}
+        if world > 1:
+            dist.barrier()
+    cpu = None
+    if rank == 0 and host_csr is not None:
+        rate, cores, kind, sample = cpu_reference_rate_stack(host_csr[0], host_csr[1], host_table, labels_np, feat,
+                                                             [args.hidden] * 3, fan, classes, args.lr,
+                                                             batch=min(args.cpu_batch, 32), steps=args.cpu_steps)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
     if rank == 0:
         wire = sent / (ms_total / K * 1e-3) / 1e9
         line = {"metric": METRIC.replace("2-layer", "3-layer"), "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
@@ -724,13 +824,16 @@ def run_products(args):
                            "l2_policy": "inputs larger than L2: fresh random targets every step", "lr": args.lr,
                            "csr_entries_rank0": entries_local, "build_s": build_s},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 4,
-                        "api": "the reference's loop (model.py:245-250) on the drop-in modules with host ids/labels"},
-                "gpu_launches": ops.LAUNCHES[0] - launches0, "clocks": clocks.summary(),
-                "roofline": None if peer else {"kernel": "all-to-all exchange (ids + feature rows + sampled tiles), rank 0 send side",
+                        "api": ("model.GraphedStep(model, B)(host ids, host labels) -> loss, .item() of it every step: "
+                                "the reference's loop body (model.py:245-250) captured as one CUDA graph") if graphed else
+                               "the reference's loop (model.py:245-250) on the drop-in modules with host ids/labels"},
+                "gpu_launches": (gstep_launches(gstep) * K) if graphed else ops.LAUNCHES[0] - launches0,
+                "clocks": clocks.summary(),
+                "roofline": roof if peer else {"kernel": "all-to-all exchange (ids + feature rows + sampled tiles), rank 0 send side",
                              "bound": "nvlink", "achieved": wire, "peak": 900.0, "unit": "GB/s", "frac": wire / 900.0,
                              "traffic": None, "bytes_sent_per_step_rank0": sent,
                              "note": "op-by-op path: the step is launch/sync-bound, not wire-bound (one host sync per lookup)"},
-                "cpu_baseline": None, "loss": loss_host}
+                "cpu_baseline": cpu, "loss": loss_host}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -176,19 +176,27 @@ sample_csr_warp_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
     if (lane == 0) cnt[i] = c;
 }
 
-// ---- dedup: mark -> count(+scan of block sums by the last block) -> compact -> remap ----
-constexpr int kChunk = 2048;       // node ids per block in the count/compact passes
+// ---- dedup over a node BITMAP: mark -> count (+ scan of block sums by the last block) -> compact -> remap -> clear ----
+// One bit per node id (N / 32 words) plus one running-rank word per bitmap word, both inside the caller's scratch.
+// Work per call: the frontier's entries (mark, remap, clear) + a popcount scan over N / 32 words (0.3 MB at 2.4 M
+// nodes; round 1 cleared and scanned a 4-byte slot per node: 9.6 MB + 2 x 9.6 MB).  The bitmap is zero on entry and
+// zero on exit: only the words a call touched are cleared again, by the ids it found.
+constexpr int kWordsPerThread = 8;
 constexpr int kScanThreads = 256;
+constexpr int kWordsPerBlock = kWordsPerThread * kScanThreads;     // 2048 words = 65 536 node ids per block
 
 __global__ void dedup_mark_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ cnt,
                                   int n_max, const int32_t* __restrict__ n_dev, int width,
-                                  int32_t* __restrict__ slot_of) {
+                                  uint32_t* __restrict__ bitmap) {
     const int n = gs_row_count(n_max, n_dev);
     const int64_t total = (int64_t)n * width;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int i = (int)(e / width), j = (int)(e - (int64_t)i * width);
-        if (cnt == nullptr || j < cnt[i]) slot_of[idx[e]] = 0;       // idempotent plain store: "present"
+        if (cnt == nullptr || j < cnt[i]) {
+            const uint32_t id = (uint32_t)idx[e];
+            atomicOr(&bitmap[id >> 5], 1u << (id & 31u));
+        }
     }
 }
 
@@ -222,15 +230,14 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total_out) {
 
 // block_counts layout: [0..nb) per-block counts -> exclusive offsets, [nb] ticket counter
 __global__ void __launch_bounds__(kScanThreads)
-dedup_count_kernel(const int32_t* __restrict__ slot_of, int num_nodes, int nb,
+dedup_count_kernel(const uint32_t* __restrict__ bitmap, int nwords, int nb,
                    int32_t* __restrict__ block_counts, int slot_base, int32_t* __restrict__ n_total_dev) {
     __shared__ int s_last;
-    const int lo = blockIdx.x * kChunk;
+    const int first = blockIdx.x * kWordsPerBlock + threadIdx.x * kWordsPerThread;
     int mine = 0;
-    for (int t = threadIdx.x; t < kChunk; t += kScanThreads) {
-        const int id = lo + t;
-        mine += (id < num_nodes && slot_of[id] == 0) ? 1 : 0;
-    }
+#pragma unroll
+    for (int t = 0; t < kWordsPerThread; ++t)
+        if (first + t < nwords) mine += __popc(bitmap[first + t]);
     int total;
     block_exclusive_scan(mine, &total);
     if (threadIdx.x == 0) {
@@ -242,7 +249,7 @@ dedup_count_kernel(const int32_t* __restrict__ slot_of, int num_nodes, int nb,
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // last block: exclusive scan over the nb block sums (nb is small: num_nodes / 2048)
+    // last block: exclusive scan over the nb block sums (nb is small: num_nodes / 65 536)
     int carry = 0;
     for (int b0 = 0; b0 < nb; b0 += kScanThreads) {
         const int b = b0 + threadIdx.x;
@@ -258,42 +265,65 @@ dedup_count_kernel(const int32_t* __restrict__ slot_of, int num_nodes, int nb,
     }
 }
 
+// uniq[rank] = id in ascending id order; word_rank[w] = slot of the first set bit of word w
 __global__ void __launch_bounds__(kScanThreads)
-dedup_compact_kernel(int32_t* __restrict__ slot_of, int num_nodes,
-                     const int32_t* __restrict__ block_counts, int slot_base,
-                     int32_t* __restrict__ uniq) {
-    const int lo = blockIdx.x * kChunk;
-    const int per = kChunk / kScanThreads;          // consecutive ids per thread keeps order
-    const int first = lo + threadIdx.x * per;
-    int flags = 0, mine = 0;
+dedup_compact_kernel(const uint32_t* __restrict__ bitmap, int nwords, const int32_t* __restrict__ block_counts,
+                     int slot_base, int32_t* __restrict__ word_rank, int32_t* __restrict__ uniq) {
+    const int first = blockIdx.x * kWordsPerBlock + threadIdx.x * kWordsPerThread;   // consecutive words per thread keep order
+    uint32_t words[kWordsPerThread];
+    int mine = 0;
 #pragma unroll
-    for (int t = 0; t < per; ++t) {
-        const int id = first + t;
-        const int f = (id < num_nodes && slot_of[id] == 0) ? 1 : 0;
-        flags |= f << t;
-        mine += f;
+    for (int t = 0; t < kWordsPerThread; ++t) {
+        words[t] = first + t < nwords ? bitmap[first + t] : 0u;
+        mine += __popc(words[t]);
     }
     int rank = block_counts[blockIdx.x] + block_exclusive_scan(mine, nullptr);
 #pragma unroll
-    for (int t = 0; t < per; ++t) {
-        if (flags >> t & 1) {
-            const int id = first + t;
-            uniq[rank] = id;
-            slot_of[id] = slot_base + rank;
-            ++rank;
+    for (int t = 0; t < kWordsPerThread; ++t) {
+        uint32_t w = words[t];
+        if (w == 0u) continue;
+        word_rank[first + t] = slot_base + rank;
+        while (w) {
+            const int bit = __ffs(w) - 1;
+            uniq[rank++] = ((first + t) << 5) + bit;
+            w &= w - 1u;
         }
     }
 }
 
 __global__ void dedup_remap_kernel(int32_t* __restrict__ idx, const int32_t* __restrict__ cnt,
                                    int n_max, const int32_t* __restrict__ n_dev, int width,
-                                   const int32_t* __restrict__ slot_of) {
+                                   const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ word_rank) {
     const int n = gs_row_count(n_max, n_dev);
     const int64_t total = (int64_t)n * width;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int i = (int)(e / width), j = (int)(e - (int64_t)i * width);
-        if (cnt == nullptr || j < cnt[i]) idx[e] = slot_of[idx[e]];
+        if (cnt == nullptr || j < cnt[i]) {
+            const uint32_t id = (uint32_t)idx[e];
+            idx[e] = word_rank[id >> 5] + __popc(bitmap[id >> 5] & ((1u << (id & 31u)) - 1u));
+        }
+    }
+}
+
+// zero exactly the bitmap words this call set (idempotent plain stores), found through the ids it produced
+__global__ void dedup_clear_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict__ n_total_dev, int slot_base,
+                                   int cap, uint32_t* __restrict__ bitmap) {
+    const int n = min(*n_total_dev - slot_base, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        bitmap[(uint32_t)uniq[i] >> 5] = 0u;
+}
+
+// plain table lookup of ids (gs_remap_ids)
+__global__ void remap_ids_kernel(int32_t* __restrict__ idx, const int32_t* __restrict__ cnt,
+                                 int n_max, const int32_t* __restrict__ n_dev, int width,
+                                 const int32_t* __restrict__ map) {
+    const int n = gs_row_count(n_max, n_dev);
+    const int64_t total = (int64_t)n * width;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / width), j = (int)(e - (int64_t)i * width);
+        if (cnt == nullptr || j < cnt[i]) idx[e] = map[idx[e]];
     }
 }
 
@@ -361,7 +391,8 @@ extern "C" int gs_sample_csr_peer(const int64_t* const* rowptrs, const int32_t* 
 }
 
 extern "C" int32_t gs_dedup_scratch_ints(int32_t num_nodes) {
-    return (num_nodes + kChunk - 1) / kChunk + 1;
+    const int nwords = (num_nodes + 31) / 32;
+    return (nwords + kWordsPerBlock - 1) / kWordsPerBlock + 1;
 }
 
 extern "C" int gs_dedup_remap(int32_t* idx, const int32_t* cnt, int32_t n_max, const int32_t* n_dev,
@@ -371,24 +402,48 @@ extern "C" int gs_dedup_remap(int32_t* idx, const int32_t* cnt, int32_t n_max, c
         n_max < 0)
         return GS_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(slot_of, 0xFF, (size_t)num_nodes * sizeof(int32_t), s);
-    if (e != cudaSuccess) return (int)e;
-    const int nb = (num_nodes + kChunk - 1) / kChunk;
+    // scratch `slot_of` (num_nodes ints, ZERO on entry and on exit): [0, nwords) the node bitmap, [nwords, 2 nwords)
+    // the rank of each word's first set bit
+    const int nwords = (num_nodes + 31) / 32;
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(slot_of);
+    int32_t* word_rank = slot_of + nwords;
+    const int nb = (nwords + kWordsPerBlock - 1) / kWordsPerBlock;
     const int64_t entries = (int64_t)n_max * width;
     int eb = (int)((entries + 255) / 256);
     if (eb > GS_NUM_SMS * 8) eb = GS_NUM_SMS * 8;
     if (eb < 1) eb = 1;
+    const int64_t cap64 = entries < num_nodes ? entries : num_nodes;
+    const int cap = (int)cap64;
     GS_PREFER_SMEM(dedup_mark_kernel);
     GS_PREFER_SMEM(dedup_count_kernel);
     GS_PREFER_SMEM(dedup_compact_kernel);
     GS_PREFER_SMEM(dedup_remap_kernel);
-    dedup_mark_kernel<<<eb, 256, 0, s>>>(idx, cnt, n_max, n_dev, width, slot_of);
+    GS_PREFER_SMEM(dedup_clear_kernel);
+    dedup_mark_kernel<<<eb, 256, 0, s>>>(idx, cnt, n_max, n_dev, width, bitmap);
     GS_LAUNCH_CHECK();
-    dedup_count_kernel<<<nb, kScanThreads, 0, s>>>(slot_of, num_nodes, nb, block_counts, slot_base, n_total_dev);
+    dedup_count_kernel<<<nb, kScanThreads, 0, s>>>(bitmap, nwords, nb, block_counts, slot_base, n_total_dev);
     GS_LAUNCH_CHECK();
-    dedup_compact_kernel<<<nb, kScanThreads, 0, s>>>(slot_of, num_nodes, block_counts, slot_base, uniq);
+    dedup_compact_kernel<<<nb, kScanThreads, 0, s>>>(bitmap, nwords, block_counts, slot_base, word_rank, uniq);
     GS_LAUNCH_CHECK();
-    dedup_remap_kernel<<<eb, 256, 0, s>>>(idx, cnt, n_max, n_dev, width, slot_of);
+    dedup_remap_kernel<<<eb, 256, 0, s>>>(idx, cnt, n_max, n_dev, width, bitmap, word_rank);
+    GS_LAUNCH_CHECK();
+    int cb = (cap + 255) / 256;
+    if (cb > GS_NUM_SMS * 4) cb = GS_NUM_SMS * 4;
+    if (cb < 1) cb = 1;
+    dedup_clear_kernel<<<cb, 256, 0, s>>>(uniq, n_total_dev, slot_base, cap, bitmap);
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+}
+
+extern "C" int gs_remap_ids(int32_t* idx, const int32_t* cnt, int32_t n_max, const int32_t* n_dev, int32_t width,
+                            const int32_t* map, void* stream) {
+    if (n_max == 0) return GS_OK;
+    if (!idx || !map || n_max < 0 || width <= 0) return GS_EINVAL;
+    const int64_t entries = (int64_t)n_max * width;
+    int eb = (int)((entries + 255) / 256);
+    if (eb > GS_NUM_SMS * 8) eb = GS_NUM_SMS * 8;
+    GS_PREFER_SMEM(remap_ids_kernel);
+    remap_ids_kernel<<<eb, 256, 0, (cudaStream_t)stream>>>(idx, cnt, n_max, n_dev, width, map);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }

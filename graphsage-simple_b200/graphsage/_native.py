@@ -67,6 +67,7 @@ SIGNATURES = {
     "gs_gather_mean_ragged": (_i32, [_ptr, _i64, _i32, _ptr, _ptr, _i32, _ptr, _i64, _ptr]),
     "gs_scatter_mean_ragged": (_i32, [_ptr, _i64, _i32, _ptr, _ptr, _i32, _ptr, _i64, _ptr]),
     "gs_advance_step": (_i32, [_ptr, _ptr]),
+    "gs_remap_ids": (_i32, [_ptr, _ptr, _i32, _ptr, _i32, _ptr, _ptr]),
     "gs_stage_next": (_i32, [_ptr, _i64, _i64, _ptr, _ptr, _ptr]),
 }
 

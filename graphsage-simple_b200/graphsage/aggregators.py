@@ -10,11 +10,28 @@ import torch
 import torch.nn as nn
 
 from . import ops, sampling
-from .functional import GatherMean, RaggedGatherMean
+from .functional import GatherMean, RaggedGatherMean, TableLookup
 from .graph import CSRGraph
 
 TABLE_INITIALIZERS = ("1hot", "node_degree")          # aggregators.py:30, 68
 RAGGED_MIN_DEGREE = 64      # un-sampled neighbourhoods wider than this use ragged tiles instead of [n, max_degree]
+
+
+_static = {"on": False}
+
+
+class static_shapes:
+    """While active, ``MeanAggregator.forward`` never reads a size back from the device: the distinct-id list keeps
+    its upper-bound length (``min(n * width, num_nodes)``, padded with id 0, which no tile entry refers to), so every
+    tensor of a train step has a shape known on the host and the step can be captured as one CUDA graph
+    (model.GraphedStep).  The padded rows are looked up / encoded and ignored."""
+
+    def __enter__(self):
+        self.prev, _static["on"] = _static["on"], True
+
+    def __exit__(self, *exc):
+        _static["on"] = self.prev
+        return False
 
 
 def _device():
@@ -103,27 +120,38 @@ class MeanAggregator(nn.Module):
             width = None
             if num_sample is None:
                 width = graph.max_degree + (1 if self.gcn else 0)
+            kw = {"step_dev": sampling.get_step_dev()} if sampling.get_step_dev() is not None else {}
             idx, cnt = graph.sample(ids, num_sample, add_self=self.gcn, seed=sampling.get_seed(),
-                                    step=sampling.get_step(), tag=self._next_tag(), width=width)
+                                    step=sampling.get_step(), tag=self._next_tag(), width=width, **kw)
             num_ids = graph.num_nodes
         # dedup (aggregators.py:52-53) and lookup of the distinct rows (aggregators.py:62-65)
+        if _static["on"]:                # no host read of the distinct count: padded, fixed-size id list
+            uniq = torch.zeros(max(min(idx.shape[0] * idx.shape[1], num_ids), 1), device=dev, dtype=torch.int32)
+            ops.dedup_remap(idx, cnt, self._dedup_scratch(num_ids, dev), uniq=uniq)
+            return GatherMean.apply(self._lookup(uniq, initializer), idx, cnt)
         uniq, n_total = ops.dedup_remap(idx, cnt, self._dedup_scratch(num_ids, dev))
-        unique_ids = uniq[:int(n_total.item())].long()
-        embed_matrix = self.features(unique_ids)
+        return GatherMean.apply(self._lookup(uniq[:int(n_total.item())], initializer), idx, cnt)
+
+    def _lookup(self, unique_ids, initializer):
+        """``embed_matrix`` of aggregators.py:62-71 for the distinct ids (int32 CUDA): rows of the frozen table, of
+        the trainable table ``self.embed`` (1hot / node_degree), or whatever the ``features`` callable returns."""
+        frozen = isinstance(self.features, nn.Embedding) and not self.features.weight.requires_grad
         if initializer in TABLE_INITIALIZERS:                          # aggregators.py:68-71
-            embed_matrix = self.embed(self._hot_index(unique_ids, embed_matrix))
-        return GatherMean.apply(embed_matrix, idx, cnt)
+            if frozen:                                                 # position of the 1: once per table, not per row
+                hot = ops.remap_ids(unique_ids.clone().view(-1, 1), None, self.hot_map()).view(-1)
+            else:
+                hot = self.features(unique_ids.long()).argmax(dim=1).to(torch.int32)
+            return TableLookup.apply(self.embed.weight, hot)
+        if isinstance(self.features, nn.Embedding):
+            return TableLookup.apply(self.features.weight, unique_ids)
+        return self.features(unique_ids.long())
 
     def _forward_ragged(self, ids, graph, initializer, dev):
         """num_sample=None (aggregators.py:47-48) on a graph with large degrees: the whole neighbourhoods as a
         ragged tile (offsets + flat ids) instead of a [n, max_degree] one; same dedup / lookup / mean."""
         off, flat = ops.take_all_csr(graph.rowptr, graph.col, ids, add_self=self.gcn)
         uniq, n_total = ops.dedup_remap(flat.view(-1, 1), None, self._dedup_scratch(graph.num_nodes, dev))
-        unique_ids = uniq[:int(n_total.item())].long()
-        embed_matrix = self.features(unique_ids)
-        if initializer in TABLE_INITIALIZERS:
-            embed_matrix = self.embed(self._hot_index(unique_ids, embed_matrix))
-        return RaggedGatherMean.apply(embed_matrix, off, flat)
+        return RaggedGatherMean.apply(self._lookup(uniq[:int(n_total.item())], initializer), off, flat)
 
     def _tile_plain(self, nodes, to_neighs, num_sample, dev, add_self=False):
         n = len(to_neighs)
@@ -151,13 +179,11 @@ class MeanAggregator(nn.Module):
             cnt[rows] += 1
         return idx, cnt, hi + 1
 
-    def _hot_index(self, unique_ids, rows):
-        """Position of the 1 in each looked-up row (aggregators.py:69).  When ``features`` is a
-        frozen nn.Embedding the positions are computed once per table, not per batch."""
+    def hot_map(self):
+        """int32 [num_nodes]: position of the 1 in each row of the frozen one-hot feature table (aggregators.py:69) --
+        the node id itself for ``1hot``, its degree for ``node_degree`` -- computed once per table, not per batch."""
         f = self.features
-        if isinstance(f, nn.Embedding) and not f.weight.requires_grad:
-            key = (f.weight.data_ptr(), f.weight._version)
-            if self._hot is None or self._hot[0] != key:
-                self._hot = (key, f.weight.argmax(dim=1))
-            return self._hot[1][unique_ids]
-        return rows.argmax(dim=1)
+        key = (f.weight.data_ptr(), f.weight._version)
+        if self._hot is None or self._hot[0] != key:
+            self._hot = (key, f.weight.argmax(dim=1).to(torch.int32).contiguous())
+        return self._hot[1]

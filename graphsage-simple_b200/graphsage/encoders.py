@@ -8,7 +8,7 @@ from torch.nn import init
 
 from . import ops, sampling
 from .aggregators import MeanAggregator, _device
-from .functional import EncoderGemm
+from .functional import EncoderGemm, TableLookup
 from .graph import CSRGraph, graph_of
 
 SIGMOID_INITIALIZERS = ("node_degree", "shared", "pagerank")      # encoders.py:58
@@ -72,7 +72,10 @@ class Encoder(nn.Module):
                     nodes, [self.adj_lists[int(node)] for node in nodes], self.num_sample,
                     initializer=self.initializer)
             if not self.gcn:
-                self_feats = self.features(ids.long())             # encoders.py:53
+                if isinstance(self.features, nn.Embedding):        # encoders.py:53
+                    self_feats = TableLookup.apply(self.features.weight, ids)
+                else:
+                    self_feats = self.features(ids.long())
                 combined = torch.cat([self_feats, neigh_feats], dim=1)
             else:
                 combined = neigh_feats

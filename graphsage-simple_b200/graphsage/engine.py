@@ -53,7 +53,7 @@ class _FrontierSet:
 class TrainEngine:
     def __init__(self, graph1, graph2, table, feat_dim, d1, d2, num_classes, k1, k2, max_batch,
                  gcn=False, agg_gcn1=False, agg_gcn2=False, act1=ops.ACT_RELU, act2=ops.ACT_RELU,
-                 uid1=1, uid2=2, device=None, use_graphs=True):
+                 uid1=1, uid2=2, device=None, use_graphs=True, embed=None, hot_map=None):
         self.dev = torch.device(device) if device is not None else (
             table.table.device if hasattr(table, "table_ptrs") else table.device)
         self.g1, self.g2 = graph1, graph2
@@ -61,6 +61,15 @@ class TrainEngine:
         # the ranks and read through NVLink peer memory by the gather kernel itself
         self.table_peer = table if hasattr(table, "table_ptrs") else None
         self.table = table.table if self.table_peer is not None else ops.aligned_rows(table)
+        # 1hot / node_degree initialisers (aggregators.py:30-31, 68-71): layer 1 aggregates rows of the TRAINABLE table
+        # ``embed`` [rows, feat_dim], reached through ``hot_map`` (node id -> position of the 1 in its one-hot feature
+        # row); the table joins the flat parameter block, its gradient is the scatter-add K4 and SGD updates it densely
+        self.trainable_table = embed is not None
+        if self.trainable_table:
+            if not gcn or hot_map is None or self.table_peer is not None:
+                raise ValueError("trainable table: gcn encoders on a local table only (the reference driver's wiring)")
+            self.hot_map = hot_map.to(torch.int32).contiguous()
+            feat_dim = embed.shape[1]
         self.F, self.d1, self.d2, self.C = int(feat_dim), int(d1), int(d2), int(num_classes)
         self.k1, self.k2 = k1, k2
         self.gcn, self.agg_gcn1, self.agg_gcn2 = bool(gcn), bool(agg_gcn1), bool(agg_gcn2)
@@ -122,6 +131,8 @@ class TrainEngine:
         self._aux = None
         # parameters + gradients: one flat block each (padded rows), module params alias into it
         shapes = [(self.d1, self.K1), (self.d2, self.K2), (self.C, self.d2)]
+        if self.trainable_table:
+            shapes.append((embed.shape[0], self.F))
         sizes = [r * ops.round4(c) for r, c in shapes]
         self.flat_w = torch.zeros(sum(sizes), device=dev)
         self.flat_g = torch.zeros(sum(sizes), device=dev)
@@ -130,8 +141,12 @@ class TrainEngine:
             views_w.append(self.flat_w[off:off + sz].view(r, ops.round4(c))[:, :c])
             views_g.append(self.flat_g[off:off + sz].view(r, ops.round4(c))[:, :c])
             off += sz
-        self.w1, self.w2, self.wc = views_w
-        self.gw1, self.gw2, self.gwc = views_g
+        self.w1, self.w2, self.wc = views_w[:3]
+        self.gw1, self.gw2, self.gwc = views_g[:3]
+        if self.trainable_table:
+            self.embed, self.gembed = views_w[3], views_g[3]
+            self.table = self.embed                      # what the layer-1 gather reads
+            self.gcomb1 = ops.empty_rows(n1_max, self.K1, dev, zero=True)
         self._graphs = {}
         self._warm = set()
         self._launch_count = {}
@@ -188,6 +203,8 @@ class TrainEngine:
                        seed=seed, step_dev=fs.step_dev, tag_head=sampling.call_tag(self.uid1, 1),
                        tag_tail=sampling.call_tag(self.uid1, 0), n_head=base, n_dev=fs.n1_dev,
                        width=self.w1_width, idx=idx1, cnt=cnt1)
+        if self.trainable_table:          # node ids -> rows of the trainable table (aggregators.py:68-71)
+            ops.remap_ids(idx1, cnt1, self.hot_map, n_dev=fs.n1_dev)
 
     @staticmethod
     def _sample(g, nodes, k, **kw):
@@ -263,6 +280,14 @@ class TrainEngine:
         self._wgrad1(fs, comb1, h1, gh1)
 
     def _wgrad1(self, fs, comb1, h1, gh1):
+        if self.trainable_table:
+            # gradient of the trainable table: d comb1 = dz1 . W1, then the scatter-add of the mean (K4) into the dense
+            # gradient block EmbeddingDenseBackward would produce (model.py:249)
+            n1_max = comb1.shape[0]
+            ops.encoder_dgrad(self.w1, h1, gh1, self.act1, self.gcomb1[:n1_max], dz=self.dz1, n_dev=fs.n1_dev)
+            self.gembed.zero_()
+            ops.scatter_mean_bwd(self.gcomb1[:n1_max], self.F, fs.idx1[:n1_max], fs.cnt1[:n1_max], self.gembed,
+                                 neigh_off=0, n_dev=fs.n1_dev)
         if self.split_self:
             ops.sage_encoder_wgrad_tc(self.table, fs.frontier1[:comb1.shape[0]], self.F, comb1, h1, gh1, self.act1,
                                       self.gw1, ws=self.tc_ws, n_dev=fs.n1_dev)
@@ -627,14 +652,15 @@ class _EngineLoss(torch.autograd.Function):
     ``loss.backward(); optimizer.step()`` (model.py:249-250) keeps working unchanged."""
 
     @staticmethod
-    def forward(ctx, loss_buf, wc, w2, w1, gwc, gw2, gw1):
-        ctx.save_for_backward(gwc, gw2, gw1)
+    def forward(ctx, loss_buf, n_params, *params_and_grads):
+        ctx.n_params = n_params
+        ctx.save_for_backward(*params_and_grads[n_params:])
         return loss_buf[0].clone()
 
     @staticmethod
     def backward(ctx, g):
-        gwc, gw2, gw1 = ctx.saved_tensors
-        return None, gwc * g, gw2 * g, gw1 * g, None, None, None
+        grads = ctx.saved_tensors
+        return (None, None) + tuple(gr * g for gr in grads) + (None,) * ctx.n_params
 
 
 def _closure_reaches(fn, target):
@@ -674,8 +700,11 @@ def engine_for(model, batch):
     peer_table = getattr(emb, "table_ptrs", None) is not None            # sharded.ShardedFeatures(peer=True)
     if not ((peer_table or (isinstance(emb, nn.Embedding) and not emb.weight.requires_grad)) and agg1.features is emb):
         return None
-    if enc1.initializer in TABLE_INITIALIZERS or enc2.initializer in TABLE_INITIALIZERS:
+    table_init = enc1.initializer in TABLE_INITIALIZERS
+    if enc2.initializer in TABLE_INITIALIZERS:
         return None
+    if table_init and not (enc1.gcn and not peer_table and hasattr(agg1, "embed")):
+        return None                      # SAGE encoders mix raw self rows with trainable-table means: op-by-op path
     from .graph import CSRGraph
     fusable = lambda g: isinstance(g, CSRGraph) or getattr(g, "rowptr_ptrs", None) is not None
     if not (fusable(enc1.graph) and fusable(enc2.graph)):
@@ -688,9 +717,13 @@ def engine_for(model, batch):
     eng = TrainEngine(enc1.graph, enc2.graph, emb if peer_table else emb.weight.data, enc1.feat_dim, enc1.embed_dim, enc2.embed_dim,
                       model.weight.shape[0], enc1.num_sample, enc2.num_sample, max(batch, 1), gcn=enc1.gcn,
                       agg_gcn1=agg1.gcn, agg_gcn2=agg2.gcn, act1=act(enc1), act2=act(enc2),
-                      uid1=agg1.uid, uid2=agg2.uid)
+                      uid1=agg1.uid, uid2=agg2.uid, embed=agg1.embed.weight.data if table_init else None,
+                      hot_map=agg1.hot_map() if table_init else None)
+    pairs = [(eng.w1, enc1.weight), (eng.w2, enc2.weight), (eng.wc, model.weight)]
+    if table_init:
+        pairs.append((eng.embed, agg1.embed.weight))
     with torch.no_grad():
-        for view, p in ((eng.w1, enc1.weight), (eng.w2, enc2.weight), (eng.wc, model.weight)):
+        for view, p in pairs:
             view.copy_(p.data)
             p.data = view
     model._engine = eng

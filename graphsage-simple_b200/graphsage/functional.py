@@ -29,6 +29,33 @@ class GatherMean(torch.autograd.Function):
         return gtable, None, None
 
 
+class TableLookup(torch.autograd.Function):
+    """rows = weight[ids]: the ``nn.Embedding`` lookups of the reference -- ``features(LongTensor(unique_nodes_list))``
+    (aggregators.py:65), ``self.embed(indices)`` (aggregators.py:71), ``self.features(nodes)`` (encoders.py:53) -- as
+    gs_gather_rows (bit-exact row copies).  Backward is EmbeddingDenseBackward (model.py:249): a dense gradient of
+    the table's shape, rows scatter-added with 128-bit reductions (gs_scatter_mean_bwd with one-entry tile rows)."""
+
+    @staticmethod
+    def forward(ctx, weight, ids):
+        w = ops.aligned_rows(weight)
+        ids = ids.to(torch.int32).contiguous()
+        out = ops.empty_rows(ids.shape[0], weight.shape[1], weight.device)
+        ops.gather_rows(w, weight.shape[1], ids, out)
+        ctx.save_for_backward(ids)
+        ctx.rows, ctx.dim = weight.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (ids,) = ctx.saved_tensors
+        gw = None
+        if ctx.needs_input_grad[0]:
+            gw = ops.empty_rows(ctx.rows, ctx.dim, gout.device, zero=True)
+            ones = torch.ones(ids.shape[0], device=gout.device, dtype=torch.int32)
+            ops.scatter_mean_bwd(ops.aligned_rows(gout), ctx.dim, ids.view(-1, 1), ones, gw, neigh_off=0)
+        return gw, None
+
+
 class RaggedGatherMean(torch.autograd.Function):
     """The same mean for un-sampled neighbourhoods of any size (num_sample=None, aggregators.py:47-48):
     row i averages table[flat[off[i] : off[i+1]]]."""

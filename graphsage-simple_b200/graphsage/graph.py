@@ -27,11 +27,11 @@ class CSRGraph:
         self.rowptr = torch.from_numpy(rowptr).to(self.device)
         self.col = torch.from_numpy(col if col.size else np.zeros(1, np.int32)).to(self.device)
 
-    def sample(self, ids, k, add_self=False, seed=0, step=0, tag=0, width=None):
+    def sample(self, ids, k, add_self=False, seed=0, step=0, tag=0, width=None, step_dev=None):
         """Fixed-width tile (idx [n, width], cnt [n]) of sampled neighbours of ``ids`` (int32 CUDA)."""
         from . import ops
         return ops.sample_csr(self.rowptr, self.col, self.num_nodes, ids, k, add_self=add_self, seed=seed,
-                              step=step, tag_head=tag, width=width)
+                              step=step, tag_head=tag, width=width, step_dev=step_dev)
 
     # ---- constructors ------------------------------------------------------------------
     @classmethod

@@ -43,6 +43,31 @@ def build_sage(features, feat_dim, hidden, adj_lists, fanouts, num_classes, gcn=
     return SupervisedGraphSage(num_classes, encs[-1]), encs
 
 
+class SGD:
+    """``torch.optim.SGD(params, lr)`` of model.py:237 (no momentum, no weight decay) on gs_sgd_step: one launch per
+    parameter, ``p = p - lr * grad`` with the same two roundings as ``p.add_(grad, alpha=-lr)``."""
+
+    def __init__(self, params, lr=0.7):
+        self.params = [p for p in params if p.requires_grad]
+        self.lr = float(lr)
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def step(self):
+        for p in self.params:
+            if p.grad is None:
+                continue
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            if p.data.is_contiguous():
+                ops.sgd_step(p.data.view(-1), g.view(-1), self.lr)
+            else:                       # a view into a padded parameter block: update a packed copy, write it back
+                w = p.data.contiguous()
+                ops.sgd_step(w.view(-1), g.view(-1), self.lr)
+                p.data.copy_(w)
+
+
 class SupervisedGraphSage(nn.Module):
 
     def __init__(self, num_classes, enc):
@@ -76,8 +101,12 @@ class SupervisedGraphSage(nn.Module):
                     b = eng.stage(nodes, labels, step)
                     eng.forward_backward(b)
                 enc2 = self.enc
-                return _EngineLoss.apply(eng.loss, self.weight, enc2.weight, enc2.base_model.weight,
-                                         eng.gwc, eng.gw2, eng.gw1)
+                params = [self.weight, enc2.weight, enc2.base_model.weight]
+                grads = [eng.gwc, eng.gw2, eng.gw1]
+                if eng.trainable_table:                                # 1hot / node_degree: aggregators.py:30-31
+                    params.append(enc2.base_model.aggregator.embed.weight)
+                    grads.append(eng.gembed)
+                return _EngineLoss.apply(eng.loss, len(params), *params, *grads)
         embeds = self.enc(nodes)
         return SoftmaxXent.apply(embeds.t(), self.weight, self._labels(labels))
 
@@ -104,6 +133,8 @@ class SupervisedGraphSage(nn.Module):
         eng = engine_for(self, max([len(nodes)] + [len(u[0]) for u in upcoming]))
         if eng is None:
             raise RuntimeError("train_step needs the canonical 2-layer wiring (model.py:214-227)")
+        if eng.trainable_table:
+            upcoming = []          # the gather reads weights the previous step updates: no gather-ahead, steps run in order
         with sampling.top_level_call() as step:
             if not upcoming and not eng.queue:
                 b = eng.stage(nodes, labels, step)
@@ -123,6 +154,72 @@ class SupervisedGraphSage(nn.Module):
                 eng.drop_queued(len(upcoming) + 1)
             eng.step_pipelined(lr, self.grad_allreduce)
         return eng.read_loss() if sync else eng.read_loss_async()
+
+
+class GraphedStep:
+    """The reference's timed unit -- ``optimizer.zero_grad(); loss = graphsage.loss(batch_nodes, labels);
+    loss.backward(); optimizer.step()`` (model.py:245-250) -- for ANY model wired from the drop-in modules (any depth
+    through the closure recursion of model.py:220-221, local or partitioned table / CSR with peer-memory lookups),
+    captured ONCE as a CUDA graph and replayed per minibatch.
+
+    The fused engine covers the canonical 2-layer wiring; deeper models (BASELINE config 5: 3 layers on a partitioned
+    graph) run through the op-by-op autograd path, which costs ~150 kernel launches and, until round 2, one host
+    read per aggregator call.  Here the aggregators run in ``static_shapes`` mode (no size ever leaves the device) and
+    the sampler step lives in device memory (``sampling.static_step``), so forward + backward + SGD is a fixed launch
+    list: the first two calls run eagerly (they size every scratch buffer), the third captures, later calls replay.
+    Data parallel (``world > 1``): the gradient all-reduce (NCCL) and the SGD step follow the replay eagerly.
+    Batches must have exactly ``batch_size`` targets."""
+
+    def __init__(self, model, batch_size, lr=0.7, world=1, n_global=None, group=None, sampler_step=0):
+        from . import sampling
+        self.model, self.lr, self.world, self.group = model, float(lr), int(world), group
+        self.n_local, self.n_global = int(batch_size), int(n_global if n_global is not None else batch_size * world)
+        dev = _device()
+        self.ids = torch.zeros(batch_size, dtype=torch.int32, device=dev)
+        self.labels = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        self.step_dev = torch.full((1,), int(sampler_step if sampler_step else sampling.get_step()), dtype=torch.int64, device=dev)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.opt = SGD(self.params, lr)
+        self.graph, self.loss, self._calls = None, None, 0
+        model.use_engine = False
+
+    def _body(self):
+        from . import sampling
+        from .aggregators import static_shapes
+        ops.advance_step(self.step_dev)
+        self.opt.zero_grad()
+        with sampling.static_step(self.step_dev), static_shapes():
+            loss = self.model.loss(self.ids, self.labels)
+        loss.backward()
+        if self.world == 1:
+            self.opt.step()
+        return loss
+
+    def __call__(self, nodes, labels):
+        """One train step on host (or device) ids / labels; returns the loss as a device scalar."""
+        if len(nodes) != self.ids.shape[0]:
+            raise ValueError("GraphedStep was built for batches of %d targets" % self.ids.shape[0])
+        self.ids.copy_(ops.as_ids(nodes, self.ids.device), non_blocking=True)
+        self.labels.copy_(self.model._labels(labels), non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        elif self._calls < 2:
+            before = ops.LAUNCHES[0]
+            self.loss = self._body()
+            self.launches_per_step = ops.LAUNCHES[0] - before      # kernels of libgsage_sm100.so in one step
+        else:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.loss = self._body()
+            self.graph = g
+            g.replay()
+        self._calls += 1
+        if self.world > 1:
+            from . import sharded
+            sharded.allreduce_grads(self.params, self.world, self.n_local, self.n_global, self.group)
+            self.opt.step()
+        return self.loss
 
 
 # ------------------------------------------------------------------------------------------------
@@ -174,7 +271,7 @@ def run_model(dataset, initializer, seed, epochs, classify="node", batch_size=12
     test, val, train = rand_indices[:test_end], rand_indices[test_end:val_end], list(rand_indices[val_end:])
     train_num = len(train)
     fused = engine_for(model, min(batch_size, train_num) if not as_run else train_num) is not None
-    optimizer = None if fused else torch.optim.SGD(filter(lambda p: p.requires_grad, model.parameters()), lr=lr)
+    optimizer = None if fused else SGD(model.parameters(), lr=lr)             # model.py:237 on gs_sgd_step
     times, losses = [], []
     for epoch in range(epochs):
         random.shuffle(train)                                                # model.py:242

@@ -79,7 +79,8 @@ class DedupScratch:
     def __init__(self, num_nodes, device):
         lib = N.load()
         self.num_nodes = int(num_nodes)
-        self.slot_of = torch.empty(self.num_nodes, device=device, dtype=torch.int32)
+        # node bitmap + per-word ranks (gs_dedup_remap): zero on entry, left zero by every call
+        self.slot_of = torch.zeros(max(self.num_nodes, 64), device=device, dtype=torch.int32)
         self.block_counts = torch.zeros(lib.gs_dedup_scratch_ints(self.num_nodes), device=device, dtype=torch.int32)
 
 
@@ -95,7 +96,7 @@ def dedup_remap(idx, cnt, scratch, slot_base=0, n_dev=None, uniq=None, n_total=N
     N.check(lib.gs_dedup_remap(N.ptr(idx), N.ptr(cnt), n_max, N.ptr(n_dev), width, scratch.num_nodes,
                                N.ptr(scratch.slot_of), N.ptr(scratch.block_counts), int(slot_base),
                                N.ptr(uniq), N.ptr(n_total), N.stream()), "gs_dedup_remap")
-    LAUNCHES[0] += 4
+    LAUNCHES[0] += 5
     return uniq, n_total
 
 
@@ -451,3 +452,13 @@ def stage_next(pool, cursor, dst):
     N.check(N.load().gs_stage_next(N.ptr(pool), pool.shape[1], pool.shape[0], N.ptr(cursor), N.ptr(dst), N.stream()),
             "gs_stage_next")
     LAUNCHES[0] += 1
+
+
+def remap_ids(idx, cnt, id_map, n_dev=None):
+    """idx[i, j] = id_map[idx[i, j]] in place for the valid entries -- see gs_remap_ids."""
+    N.require_cuda(idx, id_map)
+    n_max, width = idx.shape
+    N.check(N.load().gs_remap_ids(N.ptr(idx), N.ptr(cnt), n_max, N.ptr(n_dev), width, N.ptr(id_map), N.stream()),
+            "gs_remap_ids")
+    LAUNCHES[0] += 1
+    return idx

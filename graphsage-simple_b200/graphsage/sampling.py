@@ -6,7 +6,7 @@ function of (seed, step, tag, node id) -- ``seed`` set here, ``step`` advanced o
 top-level forward (one minibatch), ``tag`` identifying which aggregator call of that forward
 is drawing (the reference makes three independent draws per SAGE forward)."""
 
-_state = {"seed": 1, "step": 0, "depth": 0, "uid": 0}
+_state = {"seed": 1, "step": 0, "depth": 0, "uid": 0, "step_dev": None}
 
 
 def seed(s):
@@ -49,3 +49,23 @@ class top_level_call:
 
 def call_tag(uid, call_index):
     return ((int(uid) & 0xFFFFFF) << 8) | (int(call_index) & 0xFF)
+
+
+class static_step:
+    """While active, samplers read the step from the int64 device scalar ``step_dev`` instead of the host counter, so a
+    captured CUDA graph of a whole train step draws fresh neighbours on every replay (model.GraphedStep)."""
+
+    def __init__(self, step_dev):
+        self.step_dev = step_dev
+
+    def __enter__(self):
+        self.prev, _state["step_dev"] = _state["step_dev"], self.step_dev
+        return self.step_dev
+
+    def __exit__(self, *exc):
+        _state["step_dev"] = self.prev
+        return False
+
+
+def get_step_dev():
+    return _state["step_dev"]

@@ -203,19 +203,20 @@ class ShardedCSR:
         ex = exchange if exchange is not None else OwnerExchange(rank, world)
         return cls(rp, col[keep].astype(np.int32), n, int(deg.max()) if n else 0, ex, device, peer=peer)
 
-    def _local_sample(self, ids, k, add_self, seed, step, tag, width):
+    def _local_sample(self, ids, k, add_self, seed, step, tag, width, step_dev=None):
         return ops.sample_csr(self.rowptr, self.col, self.num_nodes, ids, k, add_self=add_self, seed=seed,
-                              step=step, tag_head=tag, width=width)
+                              step=step, tag_head=tag, width=width, step_dev=step_dev)
 
-    def sample(self, ids, k, add_self=False, seed=0, step=0, tag=0, width=None):
+    def sample(self, ids, k, add_self=False, seed=0, step=0, tag=0, width=None, step_dev=None):
         if width is None:
             width = (k if k is not None else self.max_degree) + (1 if add_self else 0)
         width = max(int(width), 1)
         if self.peer:
             return ops.sample_csr_peer(self.rowptr_ptrs, self.col_ptrs, self.ex.world, self.num_nodes, ids, k,
-                                       add_self=add_self, seed=seed, step=step, tag_head=tag, width=width)
+                                       add_self=add_self, seed=seed, step=step, tag_head=tag, width=width,
+                                       step_dev=step_dev)
         plan = self.ex.route(ids, emit_local=False)
-        idx, cnt = self._local_sample(plan.recv_ids, k, add_self, seed, step, tag, width)
+        idx, cnt = self._local_sample(plan.recv_ids, k, add_self, seed, step, tag, width, step_dev)
         ld = _round4(width + 1)
         tile = torch.zeros((max(idx.shape[0], 1), ld), device=idx.device, dtype=torch.int32)[:idx.shape[0]]
         tile[:, :width] = idx

@@ -74,7 +74,10 @@ GS_API int gs_sample_csr(const int64_t* rowptr, const int32_t* col, int32_t num_
  * Replaces `unique_nodes_list = list(set.union(*samp_neighs))` and the id->column dict,
  * aggregators.py:52-56.  Distinct ids of the tile, ascending, are written to uniq[0..U);
  * the tile is rewritten in place as positions slot_base + rank; *n_total_dev = slot_base + U.
- * slot_of[num_nodes] and block_counts[gs_dedup_scratch_ints(num_nodes)] are scratch.
+ * Scratch: slot_of[max(num_nodes, 64)] ints holding a node BITMAP (one bit per id) and one rank per bitmap word --
+ * ZEROED ONCE by the caller; every call leaves it zero again (only the words it touched are cleared, through the ids
+ * it found), so per call the work is the frontier's entries + a popcount scan over num_nodes / 32 words, not a clear
+ * and a scan of one 4-byte slot per node -- and block_counts[gs_dedup_scratch_ints(num_nodes)] (zeroed once).
  * cnt == NULL: every entry of idx is valid (flat ragged index array: n_max = entries, width = 1). */
 GS_API int32_t gs_dedup_scratch_ints(int32_t num_nodes);
 GS_API int gs_dedup_remap(int32_t* idx, const int32_t* cnt, int32_t n_max, const int32_t* n_dev,
@@ -293,6 +296,14 @@ GS_API int gs_sample_csr_peer(const int64_t* const* rowptrs, const int32_t* cons
                        uint64_t seed, int64_t step, const int64_t* step_dev,
                        uint32_t tag_head, uint32_t tag_tail, int32_t n_head,
                        int32_t* idx, int32_t* cnt, void* stream);
+
+/* idx[i, j] = map[idx[i, j]] for the valid entries (j < cnt[i], or all when cnt == NULL) of the rows below *n_dev.
+ * Replaces the per-row Python loop `indices = [np.where(row == 1)[0][0] for row in embed_matrix]`
+ * (aggregators.py:68-70) of the 1hot / node_degree initialisers: `map` holds, per node id, the position of the 1 in
+ * its one-hot feature row (the node id itself for 1hot, its degree for node_degree), computed once per table, so a
+ * sampled tile of node ids becomes a tile of rows of the trainable table `self.embed` (aggregators.py:30-31, 71). */
+GS_API int gs_remap_ids(int32_t* idx, const int32_t* cnt, int32_t n_max, const int32_t* n_dev, int32_t width,
+                 const int32_t* map, void* stream);
 
 /* Small device-side helpers used to keep a training step free of host round trips.       */
 GS_API int gs_advance_step(int64_t* step_dev, void* stream);                    /* ++*step_dev   */

@@ -198,6 +198,18 @@ class StackedModel:
         labels = torch.as_tensor(np.asarray(labels), dtype=torch.long).reshape(-1)
         return torch.nn.functional.cross_entropy(self.forward(nodes), labels)
 
+    def train_step(self, nodes, labels, lr=0.7):
+        """model.py:246-250: zero_grad, loss, backward, plain SGD."""
+        for p in self.parameters():
+            p.grad = None
+        loss = self.loss(nodes, labels)
+        loss.backward()
+        with torch.no_grad():
+            for p in self.parameters():
+                if p.grad is not None:
+                    p.add_(p.grad, alpha=-lr)
+        return loss.detach()
+
 
 def adj_from_csr(rowptr, col):
     """CSR -> the reference's ``adj_lists`` mapping (model.py:303-310 builds the same

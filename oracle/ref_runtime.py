@@ -92,6 +92,30 @@ def build_two_layer(table, adj_lists, feat_dim, d1, d2, num_classes, k1, k2, gcn
     return model
 
 
+def build_stack(table, adj_lists, feat_dim, hidden, fanouts, num_classes, gcn=False):
+    """Any depth, wired the way model.py:218-222 wires two layers: layer l's ``features`` is the closure
+    ``lambda nodes: enc_{l-1}(nodes).t()``.  hidden / fanouts: innermost layer first."""
+    import torch
+    import torch.nn as nn
+    agg_m, enc_m, model_m = load()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        features = nn.Embedding(table.shape[0], feat_dim)
+        features.weight = nn.Parameter(torch.as_tensor(table, dtype=torch.float32), requires_grad=False)
+        encs = []
+        for layer, (dim, k) in enumerate(zip(hidden, fanouts)):
+            if layer == 0:
+                enc = enc_m.Encoder(features, feat_dim, dim, adj_lists, agg_m.MeanAggregator(features, cuda=False),
+                                    num_sample=k, gcn=gcn, cuda=False)
+            else:
+                below = encs[-1]
+                feats = (lambda b: (lambda nodes: b(nodes).t()))(below)
+                enc = enc_m.Encoder(feats, below.embed_dim, dim, adj_lists, agg_m.MeanAggregator(feats, cuda=False),
+                                    num_sample=k, base_model=below, gcn=gcn, cuda=False)
+            encs.append(enc)
+        return model_m.SupervisedGraphSage(num_classes, encs[-1])
+
+
 def make_optimizer(model, lr):
     import torch
     return torch.optim.SGD(filter(lambda p: p.requires_grad, model.parameters()), lr=lr)      # model.py:237

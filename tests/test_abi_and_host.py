@@ -48,7 +48,7 @@ def test_argument_errors_are_codes_not_crashes(lib_path):
     assert lib.gs_sgd_step(None, None, 0.1, 10, None) == -1
     assert lib.gs_gather_rows(None, 0, 4, None, 1, None, None, 0, None) == -1
     assert lib.gs_encoder_bwd_ws_floats(1024, 256, 128) > 0
-    assert lib.gs_dedup_scratch_ints(233000) == 233000 // 2048 + 2
+    assert lib.gs_dedup_scratch_ints(233000) == (233000 + 31) // 32 // 2048 + 2      # bitmap words / 2048 per block + ticket
 
 
 def test_product_package_never_imports_the_oracle():

@@ -94,14 +94,18 @@ def test_sampler_uniform_marginals(ops):
     assert chi2 < 80.0, chi2            # 39 dof: P(chi2 > 80) ~ 1e-4
 
 
-@pytest.mark.parametrize("n_rows,width,num_nodes", [(1000, 25, 5000), (37, 3, 50), (4096, 10, 233000), (1, 1, 3)])
+@pytest.mark.parametrize("n_rows,width,num_nodes", [(1000, 25, 5000), (37, 3, 50), (4096, 10, 233000), (1, 1, 3),
+                                                    (16384, 11, 2400000), (300, 7, 65537), (5, 2, 31)])
 def test_dedup_bit_exact(ops, n_rows, width, num_nodes):
     rng = np.random.default_rng(8)
-    cnt = rng.integers(0, width + 1, n_rows).astype(np.int32)
-    idx = rng.integers(0, num_nodes, (n_rows, width)).astype(np.int32)
-    idx[np.arange(width)[None, :] >= cnt[:, None]] = -1
     scratch = ops.DedupScratch(num_nodes, "cuda")
-    for rep in range(2):                                   # the scratch re-arms itself
+    for rep in range(3):                                   # the scratch (node bitmap) is left clean by every call:
+        cnt = rng.integers(0, width + 1, n_rows).astype(np.int32)      # a DIFFERENT tile each time must not see stale bits
+        idx = rng.integers(0, num_nodes, (n_rows, width)).astype(np.int32)
+        if rep == 1:
+            idx[0, :] = num_nodes - 1                      # last id of the last bitmap word
+            idx[-1, :] = 0
+        idx[np.arange(width)[None, :] >= cnt[:, None]] = -1
         d_idx = dev(idx)
         uniq, total = ops.dedup_remap(d_idx, dev(cnt), scratch, slot_base=17)
         ru, ridx = SP.dedup_remap(idx, cnt, slot_base=17)
@@ -109,6 +113,7 @@ def test_dedup_bit_exact(ops, n_rows, width, num_nodes):
         assert u == ru.size
         assert np.array_equal(uniq.cpu().numpy()[:u], ru)
         assert np.array_equal(d_idx.cpu().numpy(), ridx)
+        assert int(scratch.slot_of[:(num_nodes + 31) // 32].abs().sum().item()) == 0      # bitmap zero again
 
 
 def test_dedup_device_row_count(ops):

@@ -187,8 +187,12 @@ def test_two_layer_against_live_oracle_with_device_samples(golden):
         assert relerr(enc1.weight.grad.cpu().numpy(), oracle.enc1.weight.grad.numpy()) < REL
 
 
+@pytest.mark.parametrize("engine", [False, True])
 @pytest.mark.parametrize("init", ["1hot", "node_degree"])
-def test_trainable_table_initialisers(golden, init):
+def test_trainable_table_initialisers(golden, init, engine):
+    """1hot / node_degree (aggregators.py:30-31, 68-71): the trainable table ``aggregator.embed`` against the
+    reference's outputs, through the op-by-op path (gs_gather_rows / scatter kernels) and through the fused engine
+    (table inside the flat parameter block, gs_remap_ids + K4 scatter as its backward)."""
     from graphsage.aggregators import MeanAggregator
     from graphsage.encoders import Encoder
     from graphsage.model import SupervisedGraphSage
@@ -211,15 +215,24 @@ def test_trainable_table_initialisers(golden, init):
         enc1.weight.copy_(torch.from_numpy(g[p + "w1"]))
         agg1.embed.weight.copy_(torch.from_numpy(g[p + "embed"]))
     assert "enc.base_model.aggregator.embed.weight" in dict(model.named_parameters())
+    model.use_engine = None if engine else False
     opt = torch.optim.SGD(filter(lambda q: q.requires_grad, model.parameters()), lr=0.7)
     opt.zero_grad()
     loss = model.loss(list(g["nodes"]), torch.LongTensor(g["labels"][g["nodes"]]))
+    assert (getattr(model, "_engine", None) is not None and model._engine.trainable_table) == engine
     loss.backward()
     assert abs(loss.item() - float(g[p + "loss"])) / abs(float(g[p + "loss"])) < REL
     assert relerr(agg1.embed.weight.grad.cpu().numpy(), g[p + "gembed"]) < REL
     assert relerr(enc1.weight.grad.cpu().numpy(), g[p + "gw1"]) < REL
     opt.step()
     assert relerr(agg1.embed.weight.detach().cpu().numpy(), g[p + "embed_new"]) < REL
+    if engine:       # the fused step (train_step: SGD on the flat block that holds the table) from the same start
+        with torch.no_grad():
+            model.weight.copy_(torch.from_numpy(g[p + "wc"])); enc2.weight.copy_(torch.from_numpy(g[p + "w2"]))
+            enc1.weight.copy_(torch.from_numpy(g[p + "w1"])); agg1.embed.weight.copy_(torch.from_numpy(g[p + "embed"]))
+        l2 = model.train_step(list(g["nodes"]), g["labels"][g["nodes"]], lr=0.7)
+        assert abs(l2 - float(g[p + "loss"])) / abs(float(g[p + "loss"])) < REL
+        assert relerr(agg1.embed.weight.detach().cpu().numpy(), g[p + "embed_new"]) < REL
 
 
 @pytest.mark.parametrize("gcn", [False, True])
@@ -472,3 +485,49 @@ def test_three_layer_train_step_matches_reference(golden):
     opt.step()
     for p, key in ((model.weight, "wc_new"), (enc3.weight, "w3_new"), (enc1.weight, "w1_new")):
         assert relerr(p.detach().cpu().numpy(), g[key]) < REL, key
+
+
+@pytest.mark.parametrize("layers", [2, 3])
+def test_graphed_step_equals_eager_op_by_op_steps(layers):
+    """model.GraphedStep (the whole op-by-op train step -- any depth -- captured as one CUDA graph: aggregators in
+    static-shape mode, sampler step in device memory) against the plain eager loop of model.py:245-250 on the same
+    device-drawn samples: losses and weights after six steps (two eager warm-ups, the capture, three replays)."""
+    from graphsage import sampling
+    from graphsage.model import build_sage, GraphedStep, SGD
+    rng = np.random.default_rng(23)
+    n, f, c, B = 900, 20, 5, 48
+    adj = {v: set() for v in range(n)}
+    for a, b in rng.integers(0, n, (6 * n, 2)):
+        adj[int(a)].add(int(b)); adj[int(b)].add(int(a))
+    table = rng.standard_normal((n, f)).astype(np.float32)
+    labels_all = rng.integers(0, c, n).astype(np.int64)
+    hidden, fan = [16, 12, 10][:layers], [3, 4, 5][:layers]
+    batches = [rng.permutation(n)[:B] for _ in range(6)]
+    out = {}
+    for mode in ("eager", "graphed"):
+        torch.manual_seed(3)
+        model, encs = build_sage(embedding_of(table), f, hidden, adj, fan, c)
+        for i, e in enumerate(encs):
+            e.aggregator.uid = 200 + i                   # same sampler tags in both models
+        sampling.seed(9)
+        losses = []
+        if mode == "eager":
+            model.use_engine = False
+            opt = SGD(model.parameters(), lr=0.2)
+            for b in batches:
+                opt.zero_grad()
+                loss = model.loss(list(b), torch.LongTensor(labels_all[b]))
+                loss.backward()
+                opt.step()
+                losses.append(loss.item())
+        else:
+            step = GraphedStep(model, B, lr=0.2)
+            for b in batches:
+                losses.append(float(step(b, labels_all[b]).item()))
+            assert step.graph is not None and step.launches_per_step > 10
+        out[mode] = (losses, [p.detach().cpu().numpy().copy() for p in model.parameters()])
+    for a, b in zip(out["eager"][0], out["graphed"][0]):
+        assert abs(a - b) <= REL * abs(a)
+    for a, b in zip(out["eager"][1], out["graphed"][1]):
+        assert relerr(b, a) < REL
+    assert out["eager"][0][0] != out["eager"][0][-1]
