@@ -180,7 +180,7 @@ class GraphedStep:
         self.step_dev = torch.full((1,), int(sampler_step if sampler_step else sampling.get_step()), dtype=torch.int64, device=dev)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.opt = SGD(self.params, lr)
-        self.graph, self.loss, self._calls = None, None, 0
+        self.graph, self.loss, self._calls, self._stream = None, None, 0, None
         model.use_engine = False
 
     def _body(self):
@@ -204,13 +204,22 @@ class GraphedStep:
         if self.graph is not None:
             self.graph.replay()
         elif self._calls < 2:
+            # eager warm-up on the side stream the capture will use (never the legacy default stream: autograd's
+            # AccumulateGrad nodes remember the stream they were created on)
+            if self._stream is None:
+                self._stream = torch.cuda.Stream()
+            self._stream.wait_stream(torch.cuda.current_stream())
             before = ops.LAUNCHES[0]
-            self.loss = self._body()
+            with torch.cuda.stream(self._stream):
+                self.loss = self._body()
+            torch.cuda.current_stream().wait_stream(self._stream)
             self.launches_per_step = ops.LAUNCHES[0] - before      # kernels of libgsage_sm100.so in one step
         else:
+            self.loss = None                     # drop the last eager autograd graph before capturing a new one
+            self.opt.zero_grad()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self._stream):
                 self.loss = self._body()
             self.graph = g
             g.replay()

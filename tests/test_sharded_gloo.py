@@ -62,7 +62,7 @@ def _worker(rank, world, port, out):
             return self.table[local_ids.long()]
 
     class CpuCSR(sharded.ShardedCSR):
-        def _local_sample(self, ids, k, add_self, seed, step, tag, width):
+        def _local_sample(self, ids, k, add_self, seed, step, tag, width, step_dev=None):
             i, c = SP.sample_csr(self.rowptr.numpy(), self.col.numpy(), ids.numpy(), -1 if k is None else k, seed, step,
                                  tag, add_self=add_self, width=width)
             return torch.from_numpy(i), torch.from_numpy(c)
