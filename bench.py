@@ -668,6 +668,38 @@ def build_partitioned_graph(n, pairs, rank, world, seed=2, chunk=1 << 24):
     return rowptr, col
 
 
+def profile_steps(step_fn, n_steps, out_path, title):
+    """Per-kernel-name device time of ``n_steps`` calls of ``step_fn`` under torch.profiler (CUPTI activity records, also
+    inside replayed CUDA graphs), written as a sorted table.  A diagnostic (shares, launch counts): never a bench value."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(n_steps):
+            step_fn()
+        torch.cuda.synchronize()
+    tmp = out_path + ".trace.json"
+    prof.export_chrome_trace(tmp)
+    tr = json.load(open(tmp))
+    os.remove(tmp)
+    evs = [e for e in tr["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+    if not evs:
+        return
+    agg = {}
+    for e in evs:
+        a = agg.setdefault(e["name"][:110], [0, 0.0])
+        a[0] += 1
+        a[1] += e["dur"]
+    span = max(e["ts"] + e["dur"] for e in evs) - min(e["ts"] for e in evs)
+    rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+    with open(out_path, "w") as f:
+        f.write("# %s\n# %d steps under torch.profiler: wall span %.1f us/step, sum of kernel time %.1f us/step, %d launches/step\n" % (
+            title, n_steps, span / n_steps, sum(v[1] for v in agg.values()) / n_steps, len(evs) // n_steps))
+        f.write("# us/step  launches/step  kernel\n")
+        for name, (cnt, dur) in rows:
+            f.write("%9.1f %6.1f  %s\n" % (dur / n_steps, cnt / n_steps, name))
+
+
 def gstep_launches(gstep):
     return getattr(gstep, "launches_per_step", 0)
 
@@ -765,6 +797,8 @@ def run_products(args):
     ms_total = float(t.item())
     value = world * B * K / (ms_total / 1e3)
     sent = (ex.bytes_sent - sent0) / K
+    if rank == 0 and os.environ.get("GSAGE_PROFILE_OUT") and world == 1:
+        profile_steps(step, 3, os.environ["GSAGE_PROFILE_OUT"], "products-shape 3-layer step, %d GPU(s), B=%d" % (world, B))
     # roofline of the partitioned path's dominant kernel: the innermost feature lookup, gs_gather_rows_peer over the
     # padded hop-3 frontier (B * 16 * 11 * 5 ids of 100 floats), (world-1)/world of whose rows cross NVLink; rank 0's
     # launch timed alone with CUDA events while the peers idle

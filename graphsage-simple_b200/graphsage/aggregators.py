@@ -79,6 +79,7 @@ class MeanAggregator(nn.Module):
         self._calls = (-1, 0)            # (step, calls made in that step) -> RNG tag
         self._scratch = None
         self._hot = None
+        self._aligned = None
 
     # ---- sampler tag bookkeeping -----------------------------------------------------------
     def _next_tag(self):
@@ -125,12 +126,43 @@ class MeanAggregator(nn.Module):
                                     step=sampling.get_step(), tag=self._next_tag(), width=width, **kw)
             num_ids = graph.num_nodes
         # dedup (aggregators.py:52-53) and lookup of the distinct rows (aggregators.py:62-65)
+        direct = self._direct_table(initializer)
+        if direct is not None:
+            # Innermost layer over a FROZEN table (model.py:214-215): nothing upstream needs a gradient, so the dedup +
+            # lookup of the distinct rows (aggregators.py:52-65) -- which exist to avoid fetching a row twice through the
+            # dense mask -- are skipped and the mean reads the sampled rows straight from the table (K2): same rows, same
+            # summation order, same bits, without materialising ``embed_matrix``.
+            n = idx.shape[0]
+            if direct[0] == "peer":
+                f = direct[1]
+                out = ops.empty_rows(n, f.dim, dev)
+                ops.gather_mean_fwd_peer(f.table_ptrs, f.ex.world, f.ld, f.dim, idx, cnt, out, neigh_off=0)
+            else:
+                t = direct[1]
+                out = ops.empty_rows(n, t.shape[1], dev)
+                ops.gather_mean_fwd(t, t.shape[1], idx, cnt, out, neigh_off=0)
+            return out
         if _static["on"]:                # no host read of the distinct count: padded, fixed-size id list
             uniq = torch.zeros(max(min(idx.shape[0] * idx.shape[1], num_ids), 1), device=dev, dtype=torch.int32)
             ops.dedup_remap(idx, cnt, self._dedup_scratch(num_ids, dev), uniq=uniq)
             return GatherMean.apply(self._lookup(uniq, initializer), idx, cnt)
         uniq, n_total = ops.dedup_remap(idx, cnt, self._dedup_scratch(num_ids, dev))
         return GatherMean.apply(self._lookup(uniq[:int(n_total.item())], initializer), idx, cnt)
+
+    def _direct_table(self, initializer):
+        """("local", table [N, F]) / ("peer", ShardedFeatures) when ``features`` is a frozen table the gather-mean kernel
+        can read by global node id, else None."""
+        if initializer in TABLE_INITIALIZERS:
+            return None
+        f = self.features
+        if isinstance(f, nn.Embedding) and not f.weight.requires_grad and f.weight.is_cuda:
+            key = (f.weight.data_ptr(), f.weight._version, tuple(f.weight.shape))
+            if self._aligned is None or self._aligned[0] != key:       # padded copy only if the rows are not 16-B aligned
+                self._aligned = (key, ops.aligned_rows(f.weight.data))
+            return ("local", self._aligned[1])
+        if getattr(f, "table_ptrs", None) is not None:                 # sharded.ShardedFeatures(peer=True)
+            return ("peer", f)
+        return None
 
     def _lookup(self, unique_ids, initializer):
         """``embed_matrix`` of aggregators.py:62-71 for the distinct ids (int32 CUDA): rows of the frozen table, of

@@ -84,11 +84,18 @@ class EncoderGemm(torch.autograd.Function):
     """h[n, d_out] = act(x . w^T): ``F.relu(self.weight.mm(combined.t()))`` of encoders.py:58-61
     in row-major form (the module returns the transposed view)."""
 
+    TC_MIN_ROWS = 512        # below this the tcgen05 kernels' fixed cost (tensor maps, TMEM allocation) is not worth it
+
     @staticmethod
     def forward(ctx, x, w, act):
         xa, wa = ops.aligned_rows(x), ops.aligned_rows(w)
         h = ops.empty_rows(x.shape[0], w.shape[0], x.device)
-        ops.encoder_fwd(xa, wa, act, h)
+        # width-128 layers on enough rows take the tcgen05 3xTF32 kernels (same 1e-5 bar), the rest the fp32 SIMT ones
+        ctx.tc = x.shape[0] >= EncoderGemm.TC_MIN_ROWS and ops.encoder_tc_supported(x.shape[1], w.shape[0])
+        if ctx.tc:
+            ops.encoder_fwd_tc(xa, wa, act, h)
+        else:
+            ops.encoder_fwd(xa, wa, act, h)
         ctx.save_for_backward(xa, wa, h)
         ctx.act = act
         return h
@@ -98,7 +105,13 @@ class EncoderGemm(torch.autograd.Function):
         xa, wa, h = ctx.saved_tensors
         gw = ops.empty_rows(wa.shape[0], wa.shape[1], gh.device)
         gx = ops.empty_rows(xa.shape[0], xa.shape[1], gh.device) if ctx.needs_input_grad[0] else None
-        ops.encoder_bwd(xa, wa, h, ops.aligned_rows(gh), ctx.act, gw, gx)
+        gha = ops.aligned_rows(gh)
+        if ctx.tc:
+            ops.encoder_wgrad_tc(xa, h, gha, ctx.act, gw)
+            if gx is not None:
+                ops.encoder_dgrad(wa, h, gha, ctx.act, gx)
+        else:
+            ops.encoder_bwd(xa, wa, h, gha, ctx.act, gw, gx)
         return gx, gw, None
 
 
