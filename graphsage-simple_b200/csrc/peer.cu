@@ -26,6 +26,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ float4 ld_peer_v4(const float4* p) {
     float4 r;      // system-scope relaxed load: never served from a stale L1 line (the addresses are reused every 2 epochs)
     asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -51,13 +57,18 @@ allreduce_sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t
     float4* mine = reinterpret_cast<float4*>(stage[rank]) + half;
     const float4* g4 = reinterpret_cast<const float4*>(g);
     for (int64_t i = lo + threadIdx.x; i < hi; i += kPeerThreads) mine[i] = g4[i];
-    __threadfence_system();
     __syncthreads();
-    // 2. raise this slice's flag at every peer, then wait for every peer's flag for the same slice
+    // 2. raise this slice's flag at every peer, then wait for every peer's flag for the same slice.
+    // The release of the flag store is cumulative over the CTA's copies ordered before it by the barrier, so only the
+    // `world` flag-writing threads fence at system scope (all 256 did in round 1).  The wait polls with RELAXED loads
+    // and acquires ONCE after it saw the flag: an acquire load per poll compiles to LDG + CCTL.IVALL, i.e. every poll
+    // of every waiting CTA invalidated the L1 of an SM that the co-resident gather of the next batch is streaming
+    // through -- measured on 8 GPUs as ~14 us of step time per peer (profiles/README.md, round 2).
     if (threadIdx.x < world) {
         st_release_sys(flags[threadIdx.x] + (int64_t)rank * gridDim.x + blockIdx.x, epoch);
         const uint32_t* f = flags[rank] + (int64_t)threadIdx.x * gridDim.x + blockIdx.x;
-        while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) { }
+        while ((int32_t)(ld_relaxed_sys(f) - epoch) < 0) __nanosleep(100);
+        fence_acq_rel_sys();
     }
     __syncthreads();
     // 3. pull, add in rank order, update
