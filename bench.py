@@ -389,7 +389,7 @@ def run_b200(args):
     # device-resident inputs: one pre-packed staging block [sampler step | labels | targets] per batch of the
     # pool, already in HBM; a step's staging is ONE device-to-device copy of 12 KB
     warm = W + 10              # every graph variant (4 frontier-set rotations x eager, capture) is replaying before the timed loop
-    total = warm + K + 2 + 16
+    total = warm + 4 * max(K, 4) + 8          # + three warm-up launches of up to K steps each
     d_blocks = torch.stack([eng.pack_stage(pool_nodes[i % pool], pool_labels[i % pool], i + 1)
                             for i in range(total)]).to(dev)
     eng.push(None, None, None, packed=(d_blocks[0], B))
@@ -412,8 +412,10 @@ def run_b200(args):
     # read from a device cursor), so K_MULTI whole pipelined steps -- each still one stage + sample chain, one gather,
     # one compute chain, one SGD / all-reduce -- replay as ONE captured graph; the per-step host work (two launches
     # per rank, 8 ranks on 16 host cores, each waiting for the slowest rank's flags every step) is paid once per
-    # K_MULTI steps.  GSAGE_BENCH_MULTI=0 restores one launch per step.
-    k_multi = int(os.environ.get("GSAGE_BENCH_MULTI", "4")) if allreduce is None else 0
+    # K_MULTI steps (default: as many of the K timed steps as fit a multiple of the four frontier sets, at most 64).
+    # GSAGE_BENCH_MULTI=0 restores one launch per step.
+    k_multi = int(os.environ.get("GSAGE_BENCH_MULTI", "64")) if allreduce is None else 0
+    k_multi = min(k_multi, K)
     k_multi -= k_multi % eng.slots
     cursor = torch.zeros(1, dtype=torch.int64, device=dev)
     multi_done = []
