@@ -4,13 +4,17 @@
 // (graphsage/model.py:237, 250).  With one process per GPU each rank holds the gradient of its share
 // of the global batch; the update every rank must apply is  p -= lr * sum_r g_r.  Instead of an NCCL
 // all-reduce followed by an SGD kernel (two launches that cannot sit inside the step's CUDA graph
-// without a collective in the capture), ONE kernel does both: every CTA publishes its slice of the
-// local gradient in a peer-mapped staging buffer, raises a per-slice flag in every peer's flag pad
-// (st.release.sys over NVLink), waits for the peers' flags for the SAME slice (ld.acquire.sys), pulls the
-// peers' slices with 128-bit loads through NVLink / NVSwitch, adds them in rank order (bit-identical on
-// every rank) and applies the update.  No grid-wide or host synchronisation; the epoch lives in device
-// memory, so the launch is CUDA-graph replayable.  Staging is double-buffered by epoch parity: a rank
-// can only reach epoch e+2 after every peer finished reading epoch e (see the argument in DESIGN.md s5).
+// without a collective in the capture), ONE kernel does both in two phases over peer-mapped memory: every CTA
+// publishes its pieces of the local gradient in the rank's staging buffer and raises a per-(rank, CTA) flag in every
+// peer's flag pad (st.release.sys over NVLink); rank r then owns slice r of the block: its CTAs wait for the peers'
+// flags (relaxed polls, one acquire), pull their piece of that slice from every rank with 128-bit loads through
+// NVLink / NVSwitch, add the `world` values in rank order and WRITE the sum into every rank's buffer (second flag);
+// finally every CTA applies the update from the broadcast sums.  Each rank moves 2 (world-1)/world of the block over
+// NVLink (round 1: every rank pulled the whole block from every peer, (world-1) x, measured ~14 us per peer); every
+// element is summed by exactly one rank in a fixed order, so the weights stay bit-identical on all ranks.  No
+// grid-wide or host synchronisation; the epoch lives in device memory, so the launch is CUDA-graph replayable.
+// Staging is double-buffered by epoch parity: a rank can only reach epoch e+2 after every peer finished epoch e
+// (see the argument in DESIGN.md s5).
 #include "gs_common.cuh"
 
 namespace {
@@ -20,11 +24,6 @@ constexpr int kPeerThreads = 256;
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
 }
 __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
     uint32_t v;
@@ -39,6 +38,22 @@ __device__ __forceinline__ float4 ld_peer_v4(const float4* p) {
     return r;
 }
 
+__device__ __forceinline__ void wait_flag(const uint32_t* f, uint32_t epoch) {
+    // RELAXED polls, ONE acquire after the flag was seen: an acquire load per poll compiles to LDG + CCTL.IVALL, i.e.
+    // every poll of every waiting CTA invalidates the L1 of an SM the co-resident gather of the next batch streams through
+    while ((int32_t)(ld_relaxed_sys(f) - epoch) < 0) __nanosleep(100);
+    fence_acq_rel_sys();
+}
+
+// Per-rank symmetric buffer (floats): in[2][n] | out[2][n] | flagsA[world * G] | flagsB[world * G]   (G = gridDim.x)
+// Two-phase exchange, so that each rank moves 2 * (world-1)/world of the block over NVLink instead of (world-1) x:
+//   1. publish    every CTA copies its pieces of the local gradient into in[parity]             flag A -> all peers
+//   2. reduce     rank r owns slice r of the block: CTA b pulls piece (r, b) of every rank's `in`, adds the
+//                 `world` values in rank order and writes the sum into EVERY rank's out[parity]  flag B -> all peers
+//   3. update     every CTA applies p -= lr * out[parity] to its pieces of all slices
+// CTA b of every rank handles piece b of every slice, so the only cross-rank dependencies are (peer q, CTA b) flags.
+// Each element is summed by exactly one rank in a fixed order and broadcast: the weights stay bit-identical on all ranks.
+// (Round 1 had every rank pull the whole block from every peer: measured ~14 us per peer, 100 us of the step at 8 GPUs.)
 // state[0] = last completed epoch, state[1] = CTA ticket of the running launch
 __global__ void __launch_bounds__(kPeerThreads)
 allreduce_sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t n4, float lr,
@@ -48,45 +63,63 @@ allreduce_sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t
     if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(state) + 1u;
     __syncthreads();
     const uint32_t epoch = s_epoch;
-    const int64_t per = (n4 + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * per;
-    const int64_t hi = lo + per < n4 ? lo + per : n4;
-    const int64_t half = (int64_t)(epoch & 1u) * n4;
+    const int G = gridDim.x, b = blockIdx.x;
+    const int64_t per_rank = (n4 + world - 1) / world;         // float4 per slice
+    const int64_t per_cta = (per_rank + G - 1) / G;            // float4 per piece
+    const int64_t in_off = (int64_t)(epoch & 1u) * n4, out_off = (2 + (int64_t)(epoch & 1u)) * n4;
+    const int64_t piece_lo = (int64_t)b * per_cta;
+    const int64_t piece_n = max((int64_t)0, min(per_cta, per_rank - piece_lo));
+    const int64_t flag_b = (int64_t)world * G;                 // flagsB follows flagsA
 
-    // 1. publish my slice
-    float4* mine = reinterpret_cast<float4*>(stage[rank]) + half;
+    // 1. publish my pieces of every slice
+    float4* my_in = reinterpret_cast<float4*>(stage[rank]) + in_off;
     const float4* g4 = reinterpret_cast<const float4*>(g);
-    for (int64_t i = lo + threadIdx.x; i < hi; i += kPeerThreads) mine[i] = g4[i];
+    for (int s = 0; s < world; ++s)
+        for (int64_t i = threadIdx.x; i < piece_n; i += kPeerThreads) {
+            const int64_t e = s * per_rank + piece_lo + i;
+            if (e < n4) my_in[e] = g4[e];
+        }
     __syncthreads();
-    // 2. raise this slice's flag at every peer, then wait for every peer's flag for the same slice.
-    // The release of the flag store is cumulative over the CTA's copies ordered before it by the barrier, so only the
-    // `world` flag-writing threads fence at system scope (all 256 did in round 1).  The wait polls with RELAXED loads
-    // and acquires ONCE after it saw the flag: an acquire load per poll compiles to LDG + CCTL.IVALL, i.e. every poll
-    // of every waiting CTA invalidated the L1 of an SM that the co-resident gather of the next batch is streaming
-    // through -- measured on 8 GPUs as ~14 us of step time per peer (profiles/README.md, round 2).
+    // the release of a flag store is cumulative over the CTA's writes ordered before it by the barrier
     if (threadIdx.x < world) {
-        st_release_sys(flags[threadIdx.x] + (int64_t)rank * gridDim.x + blockIdx.x, epoch);
-        const uint32_t* f = flags[rank] + (int64_t)threadIdx.x * gridDim.x + blockIdx.x;
-        while ((int32_t)(ld_relaxed_sys(f) - epoch) < 0) __nanosleep(100);
-        fence_acq_rel_sys();
+        st_release_sys(flags[threadIdx.x] + (int64_t)rank * G + b, epoch);
+        wait_flag(flags[rank] + (int64_t)threadIdx.x * G + b, epoch);
     }
     __syncthreads();
-    // 3. pull, add in rank order, update
-    float4* p4 = reinterpret_cast<float4*>(p);
-    for (int64_t i = lo + threadIdx.x; i < hi; i += kPeerThreads) {
-        // all peers' loads are issued before the first is consumed: one NVLink round trip, not `world`
-        float4 v[kMaxPeers];
+    // 2. reduce piece b of MY slice over all ranks (rank order), broadcast the sum
+    for (int64_t i = threadIdx.x; i < piece_n; i += kPeerThreads) {
+        const int64_t e = (int64_t)rank * per_rank + piece_lo + i;
+        if (e >= n4) break;
+        float4 v[kMaxPeers];                                   // all peers' loads in flight before the first is used
 #pragma unroll
         for (int q = 0; q < kMaxPeers; ++q)
-            if (q < world) v[q] = ld_peer_v4(reinterpret_cast<const float4*>(stage[q]) + half + i);
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < world) v[q] = ld_peer_v4(reinterpret_cast<const float4*>(stage[q]) + in_off + e);
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < kMaxPeers; ++q)
-            if (q < world) { s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w; }
-        float4 w = p4[i];
-        w.x = w.x - lr * s.x; w.y = w.y - lr * s.y; w.z = w.z - lr * s.z; w.w = w.w - lr * s.w;
-        p4[i] = w;
+            if (q < world) { sum.x += v[q].x; sum.y += v[q].y; sum.z += v[q].z; sum.w += v[q].w; }
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)
+            if (q < world) reinterpret_cast<float4*>(stage[q])[out_off + e] = sum;
     }
+    __syncthreads();
+    if (threadIdx.x < world) {
+        st_release_sys(flags[threadIdx.x] + flag_b + (int64_t)rank * G + b, epoch);
+        wait_flag(flags[rank] + flag_b + (int64_t)threadIdx.x * G + b, epoch);
+    }
+    __syncthreads();
+    // 3. update my pieces of every slice from the broadcast sums (written by the peers: read past the L1)
+    const float4* my_out = reinterpret_cast<const float4*>(stage[rank]) + out_off;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    for (int s = 0; s < world; ++s)
+        for (int64_t i = threadIdx.x; i < piece_n; i += kPeerThreads) {
+            const int64_t e = s * per_rank + piece_lo + i;
+            if (e >= n4) break;
+            const float4 sum = ld_peer_v4(my_out + e);
+            float4 w = p4[e];
+            w.x = w.x - lr * sum.x; w.y = w.y - lr * sum.y; w.z = w.z - lr * sum.z; w.w = w.w - lr * sum.w;
+            p4[e] = w;
+        }
     // 4. the last CTA closes the epoch
     __syncthreads();
     if (threadIdx.x == 0) {

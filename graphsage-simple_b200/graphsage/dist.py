@@ -62,14 +62,14 @@ class PeerAllreduceSGD:
         self.n = int(n_floats)
         assert self.n % 4 == 0
         blocks = N.load().gs_allreduce_sgd_blocks(self.n)
-        flag_words = self.world * blocks
-        total = 2 * self.n + (flag_words + 3) // 4 * 4
+        flag_words = 2 * self.world * blocks                 # flag A (published) + flag B (slice reduced) per (peer, CTA)
+        total = 4 * self.n + (flag_words + 3) // 4 * 4       # in[2][n] | out[2][n] | flags
         self.buf = symm.empty(total, dtype=torch.float32, device=device)
         self.buf.zero_()
         self.handle = symm.rendezvous(self.buf, group)
         ptrs = [int(p) for p in self.handle.buffer_ptrs]
         self.stage_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
-        self.flag_ptrs = torch.tensor([p + 4 * 2 * self.n for p in ptrs], dtype=torch.int64, device=device)
+        self.flag_ptrs = torch.tensor([p + 4 * 4 * self.n for p in ptrs], dtype=torch.int64, device=device)
         self.state = torch.zeros(2, dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
         dist.barrier(group)                      # every pad is zero before the first remote flag lands

@@ -247,9 +247,12 @@ GS_API int gs_sgd_step(float* p, const float* g, float lr, int64_t n, void* stre
 /* ---- data parallel: gradient all-reduce fused with SGD over NVLink peer memory -----------------
  * Replaces `optimizer.step()` (model.py:237, 250) when the global batch is split over `world`
  * ranks:  p -= lr * sum_r g_r, the sum taken in rank order (identical bits on every rank).
+ * Two phases over peer memory: every rank publishes its gradient, rank r sums slice r of the block over all ranks
+ * and writes the sum into every rank's buffer, every rank updates from the broadcast sums -- 2 (world-1)/world of the
+ * block crosses NVLink per rank.
  * stage_ptrs / flag_ptrs: DEVICE arrays of `world` pointers, entry q = rank q's staging buffer
- * (2 * n floats, double-buffered) / flag pad (world * gs_allreduce_sgd_blocks(n) uint32, zeroed
- * once) as mapped into THIS process (CUDA IPC / symmetric memory).  state: 2 zeroed uint32 in
+ * (4 * n floats: in[2][n] | out[2][n], double-buffered by step parity) / flag pad (2 * world *
+ * gs_allreduce_sgd_blocks(n) uint32, zeroed once) as mapped into THIS process (CUDA IPC / symmetric memory).  state: 2 zeroed uint32 in
  * local device memory (epoch, ticket).  n % 4 == 0.  Every rank must launch it once per step;
  * no host or NCCL synchronisation is involved, so the launch can sit in a captured graph.      */
 GS_API int32_t gs_allreduce_sgd_blocks(int64_t n);
