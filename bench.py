@@ -442,15 +442,16 @@ def run_b200(args):
             device_multi(i_next)
             i_next += k_multi
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
-    torch.cuda.synchronize()
+    clocks = ClockSampler(local)           # NVML init takes milliseconds and varies per rank: BEFORE the barrier, or the
+    clocks.start()                         # ranks enter the timed region skewed and the fast ones wait inside it
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     multi_done.clear()
     if n_multi:
         cursor.fill_((i_next + 2) % total)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     ev0.record()
     for _ in range(n_multi):
         device_multi(i_next)
@@ -485,19 +486,48 @@ def run_b200(args):
     def e2e_step(i):
         return model.train_step(pool_nodes[i % pool], pool_labels[i % pool], lr=lr, prefetch=nxt(i), sync=False)
 
-    for i in range(3):
-        float(e2e_step(i))
+    # Public API of the e2e loop: model.stream_trainer -- feed(host ids, host labels) per minibatch, finish() at the end;
+    # every batch's ids + labels go host -> device out of pinned memory and every step's loss comes back device -> host,
+    # k_e2e steps per graph launch (the copies are nodes of the graph).  GSAGE_E2E_MULTI=0: one train_step call per step
+    # (prefetch of the next two batches, loss of step i consumed after step i+1 was launched), the round-1 loop.
+    k_e2e = int(os.environ.get("GSAGE_E2E_MULTI", "4")) if allreduce is None else 0
+    e2e_api = ("SupervisedGraphSage.train_step(host ids, host labels, prefetch=[next two host batches], sync=False) -> loss "
+               "handle, float() of it one step later")
+    if k_e2e:
+        e2e_api = ("SupervisedGraphSage.stream_trainer(lr, steps_per_launch=%d): feed(host ids, host labels) per minibatch -> "
+                   "losses of the completed steps, finish(); per-step H2D of ids + labels and D2H of the loss are nodes of "
+                   "the %d-step graph" % (k_e2e, k_e2e))
+
+        def e2e_run(count, first):
+            tr = model.stream_trainer(lr=lr, steps_per_launch=k_e2e)
+            got = []
+            for i in range(count):
+                got += tr.feed(pool_nodes[(first + i) % pool], pool_labels[(first + i) % pool])
+            got += tr.finish()
+            assert len(got) == count
+            return got
+
+        # warm-up streams with the timed run's shape (same head of single steps, same tail): every graph the engine
+        # uses is met three times -- eager, capture, replay -- before the timed region, for both pinned-buffer variants
+        for _ in range(3):
+            e2e_run(3 + 2 * k_e2e + (K - 3) % k_e2e if K > 3 else K, 0)
+    else:
+        for i in range(3):
+            float(e2e_step(i))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ev0.record()
-    pending = None
-    for i in range(K):                      # every step's loss is read back; the read of step i is consumed
-        h = e2e_step(3 + i)                 # after step i+1 has been launched (one step of host run-ahead)
-        if pending is not None:
-            e2e_loss = float(pending)
-        pending = h
-    e2e_loss = float(pending)
+    if k_e2e:
+        e2e_loss = e2e_run(K, 3)[-1]
+    else:
+        pending = None
+        for i in range(K):                      # every step's loss is read back; the read of step i is consumed
+            h = e2e_step(3 + i)                 # after step i+1 has been launched (one step of host run-ahead)
+            if pending is not None:
+                e2e_loss = float(pending)
+            pending = h
+        e2e_loss = float(pending)
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -590,7 +620,7 @@ def run_b200(args):
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(args, B),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 + 12 * B, "d2h_bytes_per_step": 4,
-                        "api": "SupervisedGraphSage.train_step(host ids, host labels, prefetch=[next two host batches], sync=False) -> loss handle, float() of it one step later",
+                        "api": e2e_api,
                         "reference_loop_api": api_value},
                 "gpu_launches": eng.launches_per_step * K if hasattr(eng, "launches_per_step") else None,
                 "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu, "kernels_ms": kernels,
@@ -776,12 +806,12 @@ def run_products(args):
     for _ in range(W + (3 if graphed else 0)):           # graphed: two eager steps, the capture, then replays
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local)           # before the barrier (NVML init skews the ranks)
     clocks.start()
     sent0, launches0 = ex.bytes_sent, ops.LAUNCHES[0]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     ev0.record()
     for _ in range(K):

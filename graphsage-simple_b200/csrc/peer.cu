@@ -15,6 +15,7 @@
 // grid-wide or host synchronisation; the epoch lives in device memory, so the launch is CUDA-graph replayable.
 // Staging is double-buffered by epoch parity: a rank can only reach epoch e+2 after every peer finished epoch e
 // (see the argument in DESIGN.md s5).
+#include <cstdlib>
 #include "gs_common.cuh"
 
 namespace {
@@ -139,7 +140,9 @@ extern "C" int32_t gs_allreduce_sgd_blocks(int64_t n) {
     // hundred KB in total), so width, not depth; the CTAs spin only while the slowest peer catches up
     int64_t b = (n / 4 + kPeerThreads - 1) / kPeerThreads;
     if (b < 1) b = 1;
-    if (b > GS_NUM_SMS) b = GS_NUM_SMS;
+    static int cap = 0;                       // GSAGE_AR_BLOCKS: experiment knob (every rank must use the same value)
+    if (cap == 0) { cap = getenv("GSAGE_AR_BLOCKS") ? atoi(getenv("GSAGE_AR_BLOCKS")) : GS_NUM_SMS; if (cap < 1) cap = 1; }
+    if (b > cap) b = cap;
     return (int32_t)b;
 }
 

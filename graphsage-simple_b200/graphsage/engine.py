@@ -319,8 +319,8 @@ class TrainEngine:
         compute chain of set p on the current stream || gather of set p+1 || sample chain of set
         p+2.  b1 / b2 are None when the queue is shorter (tail of a run).  ``lead_lr``: apply the
         PREVIOUS step's deferred update first (data parallel, see step_pipelined); ``lr=None``: leave
-        this step's update to the next call.  ``stage=(pool, cursor)``: the inputs of the batch that is sampled in
-        this step are taken from a device-resident pool by gs_stage_next (run_device_queue)."""
+        this step's update to the next call.  ``stage``: callable(frontier set) that stages the inputs of the batch
+        sampled in this step from inside the graph (run_device_queue / run_host_queue)."""
         main = torch.cuda.current_stream()
         if b1 is not None:
             self._gstream.wait_stream(main)
@@ -330,7 +330,7 @@ class TrainEngine:
             self._sstream.wait_stream(main)
             with torch.cuda.stream(self._sstream):
                 if stage is not None:
-                    ops.stage_next(stage[0], stage[1], self.sets[(p + 2) % self.slots].stage_dev)
+                    stage(self.sets[(p + 2) % self.slots])
                 self._sample_chain(self.sets[(p + 2) % self.slots], b2)
         if lead_lr is not None:
             self._update(lead_lr)
@@ -367,7 +367,8 @@ class TrainEngine:
     def launches_per_step(self):
         """Kernels of libgsage_sm100.so in one train step (fwd+bwd+SGD), counted when enqueued."""
         c = self._launch_count
-        whole = [v for k, v in c.items() if k[0] in ("step", "pipe")] + [v // k[3] for k, v in c.items() if k[0] == "multi"]
+        whole = [v for k, v in c.items() if k[0] in ("step", "pipe")] + \
+            [v // k[3] for k, v in c.items() if k[0] in ("multi", "hostq")]
         if whole:
             return max(whole)
         parts = sum(max([v for k, v in c.items() if k[0] == nm] or [0]) for nm in ("s", "g", "cchain"))
@@ -608,15 +609,53 @@ class TrainEngine:
         if self._cstream is not None:
             main_stream.wait_stream(self._cstream)
 
+        stage_fn = lambda fs: ops.stage_next(pool, cursor, fs.stage_dev)
+
         def body():
             # one fork/join per step, as in step_pipelined.  (Round 2 also tried a dataflow capture -- each stage waiting
             # only for its true producer, gathers free-running back to back across step boundaries with the four frontier
             # sets as slack: 0.275 instead of 0.243 ms/step on one GPU, 0.300 instead of 0.259 on two; a gather that
             # never pauses slows the compute chain, which is the critical path, more than the slack buys.)
             for j in range(k):
-                self._overlapped((p0 + j) % self.slots, b, b, b, None, float(lr), stage=(pool, cursor))
+                self._overlapped((p0 + j) % self.slots, b, b, b, None, float(lr), stage=stage_fn)
         self._run(("multi", p0, b, k, float(lr), pool.data_ptr(), cursor.data_ptr()), body)
         self._slot_done = [None] * self.slots         # later pushes order themselves after everything enqueued so far
+
+    def run_host_queue(self, blocks_host, losses_host, lr):
+        """The end-to-end twin of ``run_device_queue``: ``k = len(blocks_host)`` pipelined steps as ONE graph replay whose
+        inputs come from HOST memory.  ``blocks_host`` [k, stage bytes] uint8 PINNED holds the pre-packed staging blocks
+        of the k batches that get staged during these steps (captured host->device copies, one per step, on the sampler
+        stream); ``losses_host`` [k] fp32 PINNED receives every step's loss (captured device->host copies).  The caller
+        fills ``blocks_host`` before the launch and reads ``losses_host`` after the graph's completion event; both
+        buffers are baked into the capture, so callers alternate between a few fixed (blocks, losses) pairs.  Same
+        preconditions as ``run_device_queue``."""
+        q = self.queue
+        k = int(blocks_host.shape[0])
+        if k <= 0 or k % self.slots:
+            raise ValueError("run_host_queue: the number of steps must be a positive multiple of %d" % self.slots)
+        if len(q) != 2 or q[0]["state"] != 2 or q[1]["state"] != 1 or q[0]["b"] != q[1]["b"] or self._pending_lr is None:
+            raise RuntimeError("run_host_queue needs the pipeline's steady state (run step_pipelined first)")
+        if float(lr) != self._pending_lr:
+            raise ValueError("run_host_queue: lr differs from the deferred update's lr")
+        if not (blocks_host.is_pinned() and losses_host.is_pinned()):
+            raise ValueError("run_host_queue: blocks_host / losses_host must be pinned host tensors")
+        b, p0 = q[0]["b"], self.cur
+        assert q[0]["slot"] == p0 and blocks_host.shape[1] == self.sets[0].stage_dev.numel()
+        main_stream = torch.cuda.current_stream()
+        for e in q:
+            if e["staged"] is not None:
+                main_stream.wait_event(e["staged"])
+                e["staged"] = None
+        if self._cstream is not None:
+            main_stream.wait_stream(self._cstream)
+
+        def body():
+            for j in range(k):
+                self._overlapped((p0 + j) % self.slots, b, b, b, None, float(lr),
+                                 stage=lambda fs, j=j: fs.stage_dev.copy_(blocks_host[j], non_blocking=True))
+                losses_host[j:j + 1].copy_(self.loss, non_blocking=True)
+        self._run(("hostq", p0, b, k, float(lr), blocks_host.data_ptr(), losses_host.data_ptr()), body)
+        self._slot_done = [None] * self.slots
 
     def read_loss(self):
         self.loss_host.copy_(self.loss, non_blocking=True)
@@ -641,6 +680,9 @@ class PendingLoss:
 
     def __init__(self, buf, event):
         self._buf, self._event, self._value = buf, event, None
+
+    def ready(self):
+        return self._value is not None or self._event.query()
 
     def __float__(self):
         if self._value is None:

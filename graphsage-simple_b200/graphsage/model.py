@@ -112,6 +112,10 @@ class SupervisedGraphSage(nn.Module):
 
     grad_allreduce = None   # data parallel: callable(flat_grads) run between backward and the SGD step
 
+    def stream_trainer(self, lr=0.7, steps_per_launch=4):
+        """A ``StreamTrainer`` bound to this model: ``feed(nodes, labels)`` per minibatch, ``finish()`` at the end."""
+        return StreamTrainer(self, lr, steps_per_launch)
+
     def train_step(self, nodes, labels, lr=0.7, prefetch=None, sync=True):
         """The reference's timed unit (model.py:246-250: zero_grad, loss, backward, SGD step) as
         one fused call; returns the loss as a Python float (one 4-byte device->host read).  With
@@ -154,6 +158,119 @@ class SupervisedGraphSage(nn.Module):
                 eng.drop_queued(len(upcoming) + 1)
             eng.step_pipelined(lr, self.grad_allreduce)
         return eng.read_loss() if sync else eng.read_loss_async()
+
+
+class _HostLoss:
+    """Loss of one step of a multi-step launch: a slot of the launch's pinned loss buffer, valid once its event fired."""
+
+    def __init__(self, event, buf, j):
+        self._event, self._buf, self._j, self._value = event, buf, j, None
+
+    def ready(self):
+        return self._value is not None or self._event.query()
+
+    def __float__(self):
+        if self._value is None:
+            self._event.synchronize()
+            self._value = float(self._buf[self._j])
+        return self._value
+
+
+class StreamTrainer:
+    """The reference's training loop (model.py:241-252) as a stream: ``feed(batch_nodes, labels)`` once per minibatch,
+    ``finish()`` at the end; both return the losses (floats, in order) of the steps that have completed since the last
+    call.  Every batch still goes through one ``zero_grad / loss / backward / step`` (model.py:246-250) -- its ids and
+    labels travel host -> device and its loss device -> host -- but ``steps_per_launch`` of them are submitted as ONE
+    CUDA-graph replay (``TrainEngine.run_host_queue``: the per-step host -> device copies out of pinned memory and the
+    loss read-backs are nodes of the graph), so the Python / launch cost per step is paid once per launch.  Knowing the
+    batches in advance is what a data loader gives; the reference's loop (one blocking step per iteration) cannot use it.
+    Canonical 2-layer wiring (fused engine) with equal batch sizes; anything else falls back to ``train_step`` per batch."""
+
+    def __init__(self, model, lr=0.7, steps_per_launch=4):
+        self.model, self.lr = model, float(lr)
+        self.k = max(4, int(steps_per_launch) - int(steps_per_launch) % 4)
+        self.eng, self.b = None, None
+        self.pending, self.fifo, self.fed = [], [], 0
+        self.variants, self.busy, self.turn = None, None, 0
+
+    # ---- helpers
+    def _collect(self, wait):
+        out = []
+        while self.fifo and (wait or self.fifo[0].ready()):
+            out.append(float(self.fifo.pop(0)))
+        return out
+
+    def _single(self, block):
+        eng = self.eng
+        eng.push(None, None, None, packed=(block, self.b))
+        if len(eng.queue) == 3:
+            eng.step_pipelined(self.lr, self.model.grad_allreduce)
+            self.fifo.append(eng.read_loss_async())
+
+    def _submit(self):
+        eng, k = self.eng, self.k
+        if self.variants is None:
+            # two (staging blocks, losses) pinned buffer pairs, used alternately; they are baked into the captured graphs,
+            # so they live on the engine and are shared by every stream over it
+            cache = eng.__dict__.setdefault("_stream_bufs", {})
+            if k not in cache:
+                nb = eng.sets[0].stage_dev.numel()
+                cache[k] = ([(torch.empty((k, nb), dtype=torch.uint8).pin_memory(),
+                              torch.zeros(k, dtype=torch.float32).pin_memory()) for _ in range(2)], [None, None])
+            self.variants, self.busy = cache[k]
+        v = self.turn
+        self.turn ^= 1
+        if self.busy[v] is not None:
+            self.busy[v].synchronize()             # the launch that last read these pinned buffers has finished
+        blocks, losses = self.variants[v]
+        for j, blk in enumerate(self.pending[:k]):
+            blocks[j].copy_(blk)
+        del self.pending[:k]
+        eng.run_host_queue(blocks, losses, self.lr)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.busy[v] = ev
+        self.fifo.extend(_HostLoss(ev, losses, j) for j in range(k))
+
+    # ---- public
+    def feed(self, nodes, labels):
+        from . import sampling
+        from .engine import engine_for
+        eng = engine_for(self.model, len(nodes)) if self.eng is None else self.eng
+        plain = eng is None or eng.trainable_table or self.model.grad_allreduce is not None
+        if not plain and self.b is not None and len(nodes) != self.b:
+            done = self.finish()                  # a different batch size: drain, then start a new stream
+            return done + self.feed(nodes, labels)
+        if plain:
+            return [self.model.train_step(nodes, labels, lr=self.lr)]
+        if self.eng is None:
+            self.eng, self.b = eng, len(nodes)
+            eng.reset_pipeline()
+        with sampling.top_level_call() as step:
+            block = eng.pack_stage(nodes, labels, step)
+        self.fed += 1
+        if self.fed <= 3:                         # two batches queued + one single step = the pipeline's steady state
+            self._single(block)
+        else:
+            self.pending.append(block)
+            if len(self.pending) >= self.k:
+                self._submit()
+        return self._collect(wait=False)
+
+    def finish(self):
+        if self.eng is None:
+            return []
+        eng = self.eng
+        for blk in self.pending:
+            self._single(blk)
+        self.pending = []
+        while eng.queue:                          # drain the batches still in flight
+            eng.step_pipelined(self.lr, self.model.grad_allreduce)
+            self.fifo.append(eng.read_loss_async())
+        eng.flush_update()
+        out = self._collect(wait=True)
+        self.eng, self.b, self.fed = None, None, 0
+        return out
 
 
 class GraphedStep:

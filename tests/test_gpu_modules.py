@@ -531,3 +531,38 @@ def test_graphed_step_equals_eager_op_by_op_steps(layers):
     for a, b in zip(out["eager"][1], out["graphed"][1]):
         assert relerr(b, a) < REL
     assert out["eager"][0][0] != out["eager"][0][-1]
+
+
+@pytest.mark.parametrize("n_batches", [2, 3, 9, 14])
+def test_stream_trainer_equals_sequential_train_steps(golden, n_batches):
+    """model.stream_trainer (k steps per graph launch, inputs staged from pinned host memory and losses read back by
+    copies captured IN the graph) returns the same losses, in order, and ends on the same weights as one blocking
+    train_step per batch -- for streams shorter than the pipeline, with and without a tail of single steps."""
+    from graphsage import sampling
+    g = golden("model_live")
+    gg = dict(g, w1=g["sage_w1"], w2=g["sage_w2"], wc=g["sage_wc"])
+    adj = csr_to_adj(g["rowptr"], g["col"])
+    k1, k2, B = int(g["k1"]), int(g["k2"]), 32
+    n = len(g["rowptr"]) - 1
+    rng = np.random.default_rng(41)
+    batches = [rng.permutation(n)[:B] for _ in range(n_batches)]
+    labels = [g["labels"][b] for b in batches]
+    out = {}
+    for mode in ("seq", "stream"):
+        model, enc1, enc2 = build_model(gg, False, adj, adj, k1, k2)
+        sampling.seed(5)
+        if mode == "seq":
+            losses = [model.train_step(b, l, lr=0.1) for b, l in zip(batches, labels)]
+        else:
+            tr = model.stream_trainer(lr=0.1, steps_per_launch=4)
+            losses = []
+            for b, l in zip(batches, labels):
+                losses += tr.feed(b, l)
+            losses += tr.finish()
+        torch.cuda.synchronize()
+        out[mode] = (losses, [p.detach().cpu().numpy().copy() for p in (model.weight, enc2.weight, enc1.weight)])
+    assert len(out["stream"][0]) == n_batches
+    for a, b in zip(out["seq"][0], out["stream"][0]):
+        assert abs(a - b) <= REL * abs(a)
+    for a, b in zip(out["seq"][1], out["stream"][1]):
+        assert relerr(b, a) < REL
