@@ -572,16 +572,24 @@ def run_b200(args):
             peak, which = float(_j.load(open(peaks_path))["hbm_gbs"]), "measured copy bandwidth (MEASURED_PEAKS.json)"
         # gather-1 read = (s1 + n1) * F * 4 B (neighbour rows + self rows) + the index read; the
         # combined tile the kernel WRITES is an intermediate and is not algorithmic traffic (reported separately)
-        g1_bytes = (s1 + n1) * args.feat * 4 + (s1 + 2 * n1) * 4
-        g1_write = n1 * 2 * args.feat * 4
+        in_place = bool(getattr(eng, "split_self", False))
+        if in_place:
+            # the engine's default: the self rows are gathered inside the encoder GEMMs, this kernel reads only the s1
+            # sampled neighbour rows (+ tile indices and counts) and writes the mean half of the tile
+            g1_bytes = s1 * args.feat * 4 + (s1 + n1) * 4
+            g1_write = n1 * args.feat * 4
+        else:
+            g1_bytes = (s1 + n1) * args.feat * 4 + (s1 + 2 * n1) * 4
+            g1_write = n1 * 2 * args.feat * 4
         g1_ms = kernels["gather_mean_fwd[layer1]"]
         ach = g1_bytes / (g1_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath) and (args.nodes, args.feat, args.batch, args.k1, args.k2, args.graph) == (233000, 602, 1024, 10, 25, "uniform"):
             tj = _j.load(open(tpath))           # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
-            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
-            traffic_src = tj["source"]
+            if bool(tj.get("in_place_concat", False)) == in_place:
+                traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+                traffic_src = tj["source"]
         if args.partitioned and world > 1:      # the gather's rows come over NVLink: bound by the 900 GB/s/direction ingress
             remote = (s1 + n1) * args.feat * 4 * (world - 1) / world
             nv = remote / (g1_ms * 1e-3) / 1e9
@@ -592,14 +600,19 @@ def run_b200(args):
                         "avg_launch_ms": g1_ms, "step_share": g1_ms / sum(kernels.values()),
                         "timing": "rank 0's kernel launched alone (eager, CUDA events), peers idle"}
         else:
-            roofline = {"kernel": "gather_mean_kernel (layer 1: self row + mean of k1 neighbour rows -> comb1)",
+            roofline = {"kernel": ("gather_mean_kernel (layer 1: mean of k1 sampled neighbour rows -> mean half of the tile; the self "
+                                   "rows are gathered inside the tcgen05 encoder GEMMs)") if in_place else
+                                  "gather_mean_kernel (layer 1: self row + mean of k1 neighbour rows -> comb1)",
                         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                         "peak_source": which, "traffic": traffic, "traffic_source": traffic_src,
                         "timing": "kernel launched alone (eager, CUDA events on its stream, 5 launches), same launch "
                                   "configuration as inside the pipelined step",
                         "algorithmic_bytes_per_launch": g1_bytes,
-                        "algorithmic_bytes": "SURVEY s8(d): (s1 + n1) * F * 4 row bytes + (s1 + 2 * n1) * 4 index bytes; "
-                                             "the intermediate tile the kernel writes is NOT counted",
+                        "algorithmic_bytes": ("SURVEY s8(d) for the rows THIS kernel reads: s1 * F * 4 neighbour-row bytes + (s1 + n1) * 4 "
+                                              "index bytes (the n1 self rows of s8(d)'s gather-1 are read by the GEMMs' producers, not here); "
+                                              "the intermediate tile the kernel writes is NOT counted") if in_place else
+                                             ("SURVEY s8(d): (s1 + n1) * F * 4 row bytes + (s1 + 2 * n1) * 4 index bytes; "
+                                              "the intermediate tile the kernel writes is NOT counted"),
                         "intermediate_write_bytes_per_launch": g1_write,
                         "achieved_with_intermediate_write": (g1_bytes + g1_write) / (g1_ms * 1e-3) / 1e9,
                         "frac_with_intermediate_write": (g1_bytes + g1_write) / (g1_ms * 1e-3) / 1e9 / peak,
@@ -646,7 +659,7 @@ def profile_kernels(eng, B, lr, d_nodes, d_labels, iters=5):
         def timed(*a, **kw):
             label = name[:-5] if name.endswith("_peer") else name
             if label in ("gather_mean_fwd", "encoder_fwd", "encoder_bwd", "sample_csr", "encoder_fwd_tc",
-                         "encoder_wgrad_tc"):
+                         "encoder_wgrad_tc", "sage_encoder_fwd_tc", "sage_encoder_wgrad_tc"):
                 label += "[layer1]" if (kw.get("n_dev") is not None) else "[layer2]"
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -656,7 +669,8 @@ def profile_kernels(eng, B, lr, d_nodes, d_labels, iters=5):
             return out
         setattr(ops, name, timed)
 
-    for nm in ("sample_csr", "sample_csr_peer", "gather_mean_fwd_peer", "dedup_remap", "gather_mean_fwd", "encoder_fwd", "encoder_fwd_tc", "classifier_xent",
+    for nm in ("sample_csr", "sample_csr_peer", "gather_mean_fwd_peer", "dedup_remap", "gather_mean_fwd", "encoder_fwd", "encoder_fwd_tc",
+               "sage_encoder_fwd_tc", "sage_encoder_wgrad_tc", "classifier_xent",
                "encoder_bwd", "encoder_wgrad_tc", "encoder_dgrad", "scatter_mean_bwd", "head_rows", "head_wgrad", "sgd_step"):
         wrap(nm)
     try:

@@ -28,7 +28,42 @@ __device__ __forceinline__ const float* row_ptr(const TableRef& t, int id, int64
     return t.peers[owner] + (int64_t)local * ld;       // 8-byte pointer table, L1-resident
 }
 
+// L2 eviction policies (createpolicy): the feature rows stream through once per launch (evict_first), the tile the
+// kernel writes is read again by the encoder GEMMs right after (evict_last), so that the 126 MB L2 keeps as much of the
+// 122 MB tile as it can instead of the 650 MB of rows that pass through it.  mode 0: both evict_normal (the default
+// behaviour of plain accesses).
+__device__ __forceinline__ uint64_t l2_policy(int which) {       // 0 normal, 1 evict_first, 2 evict_last
+    uint64_t p;
+    if (which == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else if (which == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg_stream_hint(const float4* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_hint_v4(float* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint_v2(float* p, float2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" :: "l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+
 // Load 4 consecutive floats of a row whose base is 16-B aligned; columns >= dim read as 0.
+__device__ __forceinline__ float4 load_chunk(const float* __restrict__ row, int c4, int dim, uint64_t pol) {
+    const int col = c4 * 4;
+    if (col + 4 <= dim) return ldg_stream_hint(reinterpret_cast<const float4*>(row) + c4, pol);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < dim) v.x = __ldg(row + col);
+    if (col + 1 < dim) v.y = __ldg(row + col + 1);
+    if (col + 2 < dim) v.z = __ldg(row + col + 2);
+    return v;
+}
+
 __device__ __forceinline__ float4 load_chunk(const float* __restrict__ row, int c4, int dim) {
     const int col = c4 * 4;
     if (col + 4 <= dim) return gs_ldg_stream(reinterpret_cast<const float4*>(row) + c4);
@@ -40,6 +75,22 @@ __device__ __forceinline__ float4 load_chunk(const float* __restrict__ row, int 
 }
 
 // Store 4 floats at dst (alignment `al` floats: 4, 2 or 1), only columns < dim.
+__device__ __forceinline__ void store_chunk(float* __restrict__ dst_row, int c4, int dim, int al, float4 v, uint64_t pol) {
+    const int col = c4 * 4;
+    float* d = dst_row + col;
+    if (col + 4 <= dim) {
+        if (al == 4) { st_hint_v4(d, v, pol); }
+        else if (al == 2) {
+            st_hint_v2(d, make_float2(v.x, v.y), pol);
+            st_hint_v2(d + 2, make_float2(v.z, v.w), pol);
+        } else { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+    } else {
+        if (col < dim) d[0] = v.x;
+        if (col + 1 < dim) d[1] = v.y;
+        if (col + 2 < dim) d[2] = v.z;
+    }
+}
+
 __device__ __forceinline__ void store_chunk(float* __restrict__ dst_row, int c4, int dim, int al, float4 v) {
     const int col = c4 * 4;
     float* d = dst_row + col;
@@ -65,10 +116,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
 gather_mean_kernel(const TableRef table, int64_t ld_table, int dim,
                    const int32_t* __restrict__ idx, const int32_t* __restrict__ cnt, int width,
                    const int32_t* __restrict__ self_ids, int n_max, const int32_t* __restrict__ n_dev,
-                   float* __restrict__ out, int64_t ld_out, int neigh_off, int out_align) {
+                   float* __restrict__ out, int64_t ld_out, int neigh_off, int out_align, int l2_mode) {
     const int n = gs_row_count(n_max, n_dev);
     const int lane = threadIdx.x & 31;
     const int nchunks = (dim + 3) >> 2;
+    const uint64_t pol_ld = l2_policy(l2_mode ? 1 : 0), pol_st = l2_policy(l2_mode ? 2 : 0);
     // grid-stride over rows: the grid is capped at a fixed number of blocks per SM so that the
     // kernel leaves room for a co-resident tensor-core CTA (engine.py pipelining)
     const int wpb = blockDim.x >> 5;
@@ -80,7 +132,7 @@ gather_mean_kernel(const TableRef table, int64_t ld_table, int dim,
 
     if (self_ids != nullptr) {          // bit-exact copy of the node's own row (encoders.py:53)
         const float* srow = row_ptr<PEER>(table, self_ids[row], ld_table);
-        for (int c4 = lane; c4 < nchunks; c4 += 32) store_chunk(orow, c4, dim, 4, load_chunk(srow, c4, dim));
+        for (int c4 = lane; c4 < nchunks; c4 += 32) store_chunk(orow, c4, dim, 4, load_chunk(srow, c4, dim, pol_ld), pol_st);
     }
     for (int c0 = 0; c0 < nchunks; c0 += 32 * CH) {
         float4 acc[CH];
@@ -98,7 +150,7 @@ gather_mean_kernel(const TableRef table, int64_t ld_table, int dim,
 #pragma unroll
                     for (int u = 0; u < CH; ++u) {
                         const int c4 = c0 + u * 32 + lane;
-                        v[b][u] = c4 < nchunks ? load_chunk(nrow, c4, dim) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[b][u] = c4 < nchunks ? load_chunk(nrow, c4, dim, pol_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
 #pragma unroll
@@ -115,7 +167,7 @@ gather_mean_kernel(const TableRef table, int64_t ld_table, int dim,
                 for (int u = 0; u < CH; ++u) {
                     const int c4 = c0 + u * 32 + lane;
                     if (c4 < nchunks) {
-                        float4 t = load_chunk(nrow, c4, dim);
+                        float4 t = load_chunk(nrow, c4, dim, pol_ld);
                         acc[u].x += t.x; acc[u].y += t.y; acc[u].z += t.z; acc[u].w += t.w;
                     }
                 }
@@ -126,7 +178,7 @@ gather_mean_kernel(const TableRef table, int64_t ld_table, int dim,
             const int c4 = c0 + u * 32 + lane;
             if (c4 < nchunks) {
                 float4 m = make_float4(acc[u].x * inv, acc[u].y * inv, acc[u].z * inv, acc[u].w * inv);
-                store_chunk(orow + neigh_off, c4, dim, out_align, m);
+                store_chunk(orow + neigh_off, c4, dim, out_align, m, pol_st);
             }
         }
     }
@@ -224,8 +276,9 @@ int launch_gather_mean(const TableRef& table, bool peer, int64_t ld_table, int32
     // (Round 2: a column-split variant -- 2 warps per row, 3 chunks x 3 neighbours per lane in 64 registers, 16 warps
     // per SM = 72 KB in flight -- measured the SAME 0.183 ms: with the 164 KB shared / 64 KB L1 split the co-resident
     // GEMM needs, the bound is the L1's outstanding-request capacity, not warps x registers; profiles/README.md.)
-    static int bps = 0, wpb = 0, carve = 0;
+    static int bps = 0, wpb = 0, carve = 0, l2_mode = 0;
     if (bps == 0) {
+        l2_mode = getenv("GSAGE_GATHER_L2") ? atoi(getenv("GSAGE_GATHER_L2")) : 0;
         // L1/shared split preference (percent of shared; 1 = max shared, 0 = driver default).  The split can only
         // change on an idle SM, so a resident gather with the default (L1-heavy) split keeps the 145 KB GEMM CTAs
         // and the 175 KB head CTAs out; max-shared starves the gather's outstanding loads of L1.  72 % = 164 KB
@@ -247,7 +300,7 @@ int launch_gather_mean(const TableRef& table, bool peer, int64_t ld_table, int32
         if (!d__ && carve) { cudaFuncSetAttribute((gather_mean_kernel<CH, NB, P>), cudaFuncAttributePreferredSharedMemoryCarveout, \
                                                   carve == 1 ? (int)cudaSharedmemCarveoutMaxShared : carve); d__ = true; } \
         gather_mean_kernel<CH, NB, P><<<grid, block, 0, s>>>(table, ld_table, dim, idx, cnt, width, \
-            self_ids, n_max, n_dev, out, ld_out, neigh_off, align); } while (0)
+            self_ids, n_max, n_dev, out, ld_out, neigh_off, align, l2_mode); } while (0)
 #define GS_GM(CH, NB) do { if (peer) GS_GM1(CH, NB, true); else GS_GM1(CH, NB, false); } while (0)
     if (nchunks <= 32) { GS_GM(1, 8); }
     else if (nchunks <= 64) { GS_GM(2, 4); }

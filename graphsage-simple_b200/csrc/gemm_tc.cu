@@ -23,8 +23,8 @@
 //
 // Per CTA (320 threads, 1 CTA/SM): 3-stage smem ring of 48 KB (X raw, Y_hi, Y_lo), TMEM =
 // 2 main accumulators + 1 correction accumulator (3 x 128 columns) + 2 A slots (2 x 64 columns).
-//   warp 0      producer: TMA tiles (one lane) + gathered table rows (cp.async spread over the lanes)
-//   warps 2..5  splitter (smem -> registers -> TMEM A slot), later the epilogue
+//   warp 0      TMA producer (W / dZ tiles, X tiles that exist in memory)
+//   warps 2..9  two splitter groups (smem -> registers -> TMEM A slot; gathered X tiles: cp.async refill), later the epilogue
 //   warp 1      MMA issuer (one lane): per stage 4 k-steps x 3 tcgen05.mma, tcgen05.commit
 #include <cuda.h>
 #include <cstdlib>
@@ -44,7 +44,7 @@ constexpr int kChunk = 32;            // reduction elements per stage: 32 fp32 =
 constexpr int kOperandBytes = kTile * kChunk * 4;          // 16 KB
 constexpr int kXBytes = kOperandBytes;
 constexpr int kStageBytes = kXBytes + 2 * kOperandBytes;   // X raw, Y_hi, Y_lo (pre-split in global memory)
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers + tmem slot*/;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers + tmem slot*/ + 512 /*NT: table rows of the tile*/;
 constexpr int kThreads = 320;          // TMA, MMA, 2 x 4 X-splitter/epilogue warps
 // The tensor core rounds toward zero when it adds a k-step into the fp32 accumulator: measured
 // bias ~1 ulp per tcgen05.mma (profiles/README.md), i.e. ~1e-5 relative after the 450 MMAs of a
@@ -90,9 +90,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 // it stays an option (GSAGE_SPLIT_SELF=1), not the default.
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes));
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {      // arrives once this thread's copies have landed
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -148,7 +145,6 @@ struct TcArgs {
     const int32_t* self_ids;   // [n_max] table row of every X row
     int self_units;
     int self_cols;             // feature width F (columns of the self half; the mean half follows at column F of W / dW)
-    int prefetch;              // gathered rows are pulled into L2 this many chunks ahead of the ring
     int debug;                 // experiment switches (GSAGE_TC_DEBUG), 0 in production
     long long* trace;          // optional [64 chunks][16 events] clock64 trace of block 0 (GSAGE_TC_TRACE)
 };
@@ -236,8 +232,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            // producer's expect_tx arrive; with gathered rows every producer lane arrives once more (its cp.async group)
-            mbar_init(bars + 8 * (kBarFull + s), gathers ? 33 : 1);
+            // producer's expect_tx arrive; in a CTA that gathers rows, every chunk additionally gets one arrival from each
+            // of the 128 threads of the splitter group on refill duty (its cp.async group, or a plain arrive for a TMA chunk)
+            mbar_init(bars + 8 * (kBarFull + s), gathers ? 1 + 128 : 1);
             mbar_init(bars + 8 * (kBarEmpty + s), 1);          // tcgen05.commit
         }
         for (int a = 0; a < kASlots; ++a) {
@@ -247,6 +244,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         mbar_init(bars + 8 * kBarAccum, 1);
         for (int st = 0; st < kStages; ++st) mbar_init(bars + 8 * (kBarYReady + st), 4);   // the chunk's 4 X-splitter warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    int32_t* tile_ids = reinterpret_cast<int32_t*>(gen_base + kStages * kStageBytes + 256);
+    if (!TN && gathers && threadIdx.x < kTile) {               // table row of every row of this tile (rows past n: any valid row)
+        const int r = x_fixed + (int)threadIdx.x;
+        tile_ids[threadIdx.x] = __ldg(g.self_ids + (r < n ? r : n - 1));
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols));
@@ -259,83 +261,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t tmem_a = tmem + kAccs * kTile;              // first A-staging column
 
     if (warp == 0) {
-        // ---------------------------------------------------------------- producer (TMA tiles + gathered rows)
-        // The whole warp runs the loop: a gathered chunk is 32 coalesced 16-B cp.async per lane.
-        const int64_t ld_t = g.ld_table;
-        int my_rows[kTile / 32];                               // NT: table rows lane, lane + 32, ... of this tile
-        if (!TN && gathers) {
-#pragma unroll
-            for (int i = 0; i < kTile / 32; ++i) {
-                const int r = x_fixed + lane + 32 * i;
-                my_rows[i] = __ldg(g.self_ids + (r < n ? r : n - 1));        // rows past n: any valid row (never stored)
-            }
-        }
-        // Gathered rows are random 128-B (NT) / 512-B (TN) pieces of the table in HBM: each chunk's pieces are pulled
-        // into L2 `pf` chunks before the ring asks for them, so the ring's cp.async see L2 latency
-        const int pf = gathers ? g.prefetch : 0;
-        auto prefetch_chunk = [&](int c) {
-            if (!TN) {
-                if (c >= self_chunks) return;
-                const int col = c * kChunk;
-                if (col >= (int)ld_t) return;
-                const int last = min(col + kChunk, (int)ld_t) - 1;
-#pragma unroll
-                for (int i = 0; i < kTile / 32; ++i) {
-                    const float* row = g.table + (int64_t)my_rows[i] * ld_t;
-                    prefetch_l2(row + col);
-                    prefetch_l2(row + last);                   // rows are not 128-B aligned: a piece may straddle two lines
-                }
-            } else {
-                const int r = (chunk_begin + c) * kChunk + lane;
-                if (c >= nchunks || r >= n) return;
-                const float* row = g.table + (int64_t)__ldg(g.self_ids + r) * ld_t + x_fixed;
-                const int w = min(kTile, (int)ld_t - x_fixed);
-                for (int o = 0; o < w; o += 32) prefetch_l2(row + o);
-                prefetch_l2(row + w - 1);
-            }
-        };
-        for (int c = 0; c < pf; ++c) prefetch_chunk(c);
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c % kStages, it = c / kStages;
-            if (pf) prefetch_chunk(c + pf);
-            mbar_wait(bars + 8 * (kBarEmpty + s), (it & 1) ^ 1);
-            TC_TRACE(0, c);
-            const uint32_t st = base + s * kStageBytes;
-            const uint32_t full = bars + 8 * (kBarFull + s);
-            if (g.debug & 8) { if (lane == 0 || gathers) mbar_arrive(full); if (lane == 0 && gathers) mbar_arrive(full); continue; }
-            if (!TN) {
-                if (c < self_chunks) {
-                    // 128 table rows x 128 B in the SWIZZLE_128B layout the TMA tiles have: 16-B piece p of row r at
-                    // r * 128 + ((p ^ (r % 8)) * 16).  Lanes 8s..8s+7 copy the 8 pieces of one row (one 128-B line).
-                    const int col = c * kChunk;
-                    if (lane == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        // W / dZ tiles always; the X tile unless this chunk's rows are gathered from the feature table (then the
+        // splitter groups load it, see "refill duty" below).
+        if (lane == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % kStages, it = c / kStages;
+                mbar_wait(bars + 8 * (kBarEmpty + s), (it & 1) ^ 1);
+                TC_TRACE(0, c);
+                const uint32_t st = base + s * kStageBytes;
+                const uint32_t full = bars + 8 * (kBarFull + s);
+                if ((g.debug & 8) && !gathers) { mbar_arrive(full); continue; }
+                if (!TN) {
+                    if (c < self_chunks) {
+                        const int col = c * kChunk;
                         mbar_expect_tx(full, 2 * kOperandBytes);
                         tma_load_2d(st + kXBytes, &map_shi, col, 0, full);                 // W_hi, self columns
                         tma_load_2d(st + kXBytes + kOperandBytes, &map_slo, col, 0, full); // W_lo
-                    }
-                    const int piece = lane & 7, sub = lane >> 3;
-                    const uint32_t src_bytes = (col + 4 * piece < (int)ld_t) ? 16u : 0u;   // past the row: zero-fill
-                    const float* src0 = g.table + (src_bytes ? col + 4 * piece : 0);
-#pragma unroll
-                    for (int i = 0; i < kTile / 4; ++i) {
-                        const int r = 4 * i + sub;
-                        const int id = __shfl_sync(0xffffffffu, my_rows[i / 8], 4 * (i % 8) + sub);
-                        cp_async16(st + (uint32_t)(r * 128 + ((piece ^ (r & 7)) << 4)), src0 + (int64_t)id * ld_t, src_bytes);
-                    }
-                    cp_async_arrive(full);
-                } else {
-                    if (lane == 0) {
+                    } else {
                         const int kc = (c - self_chunks) * kChunk;
                         mbar_expect_tx(full, 3 * kOperandBytes);
                         tma_load_2d(st, &map_x, kc, x_fixed, full);                        // X rows (SW128)
                         tma_load_2d(st + kXBytes, &map_yhi, kc, 0, full);                  // W_hi (SW128, K-major)
                         tma_load_2d(st + kXBytes + kOperandBytes, &map_ylo, kc, 0, full);  // W_lo
                     }
-                    if (gathers) mbar_arrive(full);            // keeps the per-chunk arrival count uniform (33)
-                }
-            } else {
-                const int kc = (chunk_begin + c) * kChunk;
-                if (lane == 0) {
+                } else {
+                    const int kc = (chunk_begin + c) * kChunk;
                     mbar_expect_tx(full, (self_tile ? 2 : 3) * kOperandBytes);
                     if (!self_tile) tma_load_2d(st, &map_x, x_fixed, kc, full);            // X [32 rows][128 cols], linear
 #pragma unroll
@@ -344,23 +295,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         tma_load_2d(st + kXBytes + kOperandBytes + b * 4096, &map_ylo, 32 * b, kc, full);
                     }
                 }
-                if (self_tile) {
-                    // row kc + i of X = table row self_ids[kc + i], columns [x_fixed, x_fixed + 128): instruction i copies
-                    // one row's 512 contiguous bytes (lane = 16-B piece) into the linear [32][128] tile
-                    const int r = kc + lane;
-                    const int my_id = __ldg(g.self_ids + (r < n ? r : n - 1));             // rows past n meet dZ rows of 0
-                    const uint32_t src_bytes = (x_fixed + 4 * lane < (int)ld_t) ? 16u : 0u;
-                    const float* src0 = g.table + (src_bytes ? x_fixed + 4 * lane : 0);
-                    int ids[kChunk];
-#pragma unroll
-                    for (int i = 0; i < kChunk; ++i) ids[i] = __shfl_sync(0xffffffffu, my_id, i);
-#pragma unroll
-                    for (int i = 0; i < kChunk; ++i)
-                        cp_async16(st + (uint32_t)(i * (kTile * 4) + lane * 16), src0 + (int64_t)ids[i] * ld_t, src_bytes);
-                    cp_async_arrive(full);
-                }
+                TC_TRACE(1, c);
             }
-            TC_TRACE(1, c);
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
@@ -410,6 +346,47 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int row = q * 32 + lane;                         // A/accumulator row handled by this thread
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t slot = tmem_a + lane_base + grp * kASlotCols;
+        // ---- refill duty (CTAs that gather rows of the feature table).  The X region of a stage is free the moment the
+        // group that split chunk c has read it (the MMAs only read the W region), so that group loads the X tile of chunk
+        // c + kStages into it right away: 128 threads x 8 coalesced 16-B cp.async instead of one producer warp x 32
+        // (measured: ~45 cycles per LDGSTS from one warp made the gathered chunk the whole chunk period).  Every chunk
+        // gets exactly one duty -- cp.async + arrive-on-completion for a gathered chunk, a plain arrive for a TMA chunk --
+        // by group (c + kStages) % 2; chunks < kStages are served before the loop.
+        const int tg = (warp - 2 - 4 * grp) * 32 + lane;       // thread index within the group, 0..127
+        const int64_t ld_t = g.ld_table;
+        auto refill = [&](int c) {
+            const uint32_t st = base + (c % kStages) * kStageBytes;
+            const uint32_t full = bars + 8 * (kBarFull + c % kStages);
+            if (!TN) {
+                if (c >= self_chunks) { mbar_arrive(full); return; }
+                // 128 table rows x 128 B in the SWIZZLE_128B layout of the TMA tiles: piece p of row r at r * 128 + ((p ^ (r % 8)) * 16)
+                const int col = c * kChunk, piece = tg & 7, sw = (tg >> 3) & 7;
+                const uint32_t src_bytes = (col + 4 * piece < (int)ld_t) ? 16u : 0u;       // past the row: zero-fill
+                const float* src0 = g.table + (src_bytes ? col + 4 * piece : 0);
+                const uint32_t dst0 = st + (uint32_t)((tg >> 3) * 128 + ((piece ^ sw) << 4));
+#pragma unroll
+                for (int i = 0; i < 8; ++i)                                                // tile row 16 i + tg / 8
+                    cp_async16(dst0 + (uint32_t)(16 * i * 128), src0 + (int64_t)tile_ids[16 * i + (tg >> 3)] * ld_t, src_bytes);
+            } else {
+                // rows kc .. kc + 31 of X = table rows self_ids[kc ..], columns [x_fixed, x_fixed + 128): linear [32][128] tile
+                const int kc = (chunk_begin + c) * kChunk, piece = tg & 31;
+                const uint32_t src_bytes = (x_fixed + 4 * piece < (int)ld_t) ? 16u : 0u;
+                const float* src0 = g.table + (src_bytes ? x_fixed + 4 * piece : 0);
+                int ids[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = kc + 4 * i + (tg >> 5);
+                    ids[i] = __ldg(g.self_ids + (r < n ? r : n - 1));      // rows past n meet dZ rows of 0
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    cp_async16(st + (uint32_t)((4 * i + (tg >> 5)) * (kTile * 4) + piece * 16), src0 + (int64_t)ids[i] * ld_t, src_bytes);
+            }
+            cp_async_arrive(full);
+        };
+        if (gathers)
+            for (int c = 0; c < kStages && c < nchunks; ++c)
+                if ((c + kStages) % kASlots == grp) refill(c);
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % kStages, it = c / kStages;
             // EVERY chunk's full barrier is observed, also the other group's: a parity wait only tells phase k
@@ -464,6 +441,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + 8 * (kBarYReady + s));   // same per-stage barrier as the Y splitter
+            if (gathers) {
+                // all four warps of the group are done with this stage's X region: refill it for chunk c + kStages
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (c + kStages < nchunks) refill(c + kStages);
+            }
         }
         if (nchunks > 0) {
             mbar_wait(bars + 8 * kBarAccum, 0);
@@ -619,9 +601,6 @@ int tc_debug() {
     if (v < 0) v = getenv("GSAGE_TC_DEBUG") ? atoi(getenv("GSAGE_TC_DEBUG")) : 0;
     return v;
 }
-int tc_prefetch() {
-    return getenv("GSAGE_TC_PREFETCH") ? atoi(getenv("GSAGE_TC_PREFETCH")) : 0;
-}
 long long* tc_trace() {
     return getenv("GSAGE_TC_TRACE") ? (long long*)strtoull(getenv("GSAGE_TC_TRACE"), nullptr, 10) : nullptr;
 }
@@ -693,7 +672,7 @@ int launch_fwd(const XSource& xs, const float* w, int64_t ld_w, int32_t d_out, i
         attr_set = true;
     }
     TcArgs g{n_max, n_dev, xs.k_dense, act, h, ld_h, 0, 0, xs.table, xs.ld_table, xs.self_ids,
-             sc ? (sc + kChunk - 1) / kChunk : 0, sc, tc_prefetch(), tc_debug(), tc_trace()};
+             sc ? (sc + kChunk - 1) / kChunk : 0, sc, tc_debug(), tc_trace()};
     tc_gemm_kernel<false><<<(n_max + kTile - 1) / kTile, kThreads, kSmemBytes, s>>>(mx, mh, ml, msh, msl, g);
     GS_LAUNCH_CHECK();
     return GS_OK;
@@ -730,7 +709,7 @@ int launch_wgrad(const XSource& xs, const float* h, int64_t ld_h, const float* g
         attr_set = true;
     }
     TcArgs g{n_max, n_dev, xs.k_dense, GS_ACT_NONE, part, ldw, rps, (int64_t)d_out * ldw, xs.table, xs.ld_table, xs.self_ids,
-             self_tiles, sc, tc_prefetch(), tc_debug(), nullptr};
+             self_tiles, sc, tc_debug(), nullptr};
     dim3 grid(tiles, splits);
     tc_gemm_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(mx, mh, ml, mh, ml, g);
     GS_LAUNCH_CHECK();

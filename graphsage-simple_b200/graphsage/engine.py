@@ -89,14 +89,13 @@ class TrainEngine:
         self.K2 = self.d1 if self.gcn else 2 * self.d1
         # layer 1 runs on the tcgen05 path when the shape qualifies (d1 == 128, K1 >= 32)
         self.tc1 = ops.encoder_tc_supported(self.K1, self.d1)
-        # ... and, in SAGE mode on a local table, can consume the concat in place ([table[v] | mean] never written:
-        # gs_sage_encoder_*_tc).  Measured on B200 (profiles/README.md, round 2): -122 MB of HBM traffic per step and a
-        # 25 % shorter gather, but the GEMMs' single producer warp cannot issue the 32 row-gather copies per chunk fast
-        # enough (forward 86 vs 72 us, weight gradient 104 vs 71 us) and the step gets SLOWER (0.268 vs 0.241 ms), so
-        # it is opt-in (GSAGE_SPLIT_SELF=1), parity-tested either way.
+        # ... and, in SAGE mode on a local table, consumes the concat in place: only the neighbour-mean half of the
+        # layer-1 tile is written, the self rows `self.features(nodes)` (encoders.py:53) are gathered from the feature
+        # table inside the GEMMs (gs_sage_encoder_*_tc).  -122 MB of HBM traffic per Reddit-shape step, gather 0.183 ->
+        # 0.135 ms, step 0.244 -> 0.230 ms (profiles/README.md R2.3).  GSAGE_SPLIT_SELF=0 keeps the [self | mean] tile.
         self.split_self = (self.tc1 and not self.gcn and self.table_peer is None and
                            ops.encoder_tc_supported(self.F, self.d1) and
-                           bool(int(__import__('os').environ.get('GSAGE_SPLIT_SELF', '0'))))
+                           bool(int(__import__('os').environ.get('GSAGE_SPLIT_SELF', '1'))))
         self.sets = [_FrontierSet(self)]           # sets 2 and 3 are created on first pipelined use
         self.cur = 0
         self.loss_host = torch.empty(1, dtype=torch.float32).pin_memory()

@@ -67,16 +67,17 @@ def test_fused_train_step_matches_reference_at_baseline_widths(golden, name):
     assert tuple(scores.shape) == g["scores"].shape and torch.isfinite(scores).all()
 
 
+@pytest.mark.parametrize("in_place", [True, False])
 @pytest.mark.parametrize("name", ["bs_reddit", "bs_pubmed"])
-def test_in_place_concat_variant_matches_reference(golden, name, monkeypatch):
-    """GSAGE_SPLIT_SELF=1: the engine keeps only the neighbour-mean half of the layer-1 tile and the tcgen05 GEMMs
-    gather the self rows from the feature table in their producer warp (gs_sage_encoder_fwd_tc / _wgrad_tc,
-    encoders.py:53-61 as one op).  Same reference outputs."""
-    monkeypatch.setenv("GSAGE_SPLIT_SELF", "1")
+def test_in_place_concat_and_materialised_tile_match_reference(golden, name, in_place, monkeypatch):
+    """Default (GSAGE_SPLIT_SELF=1): the engine keeps only the neighbour-mean half of the layer-1 tile and the tcgen05
+    GEMMs gather the self rows from the feature table themselves (gs_sage_encoder_fwd_tc / _wgrad_tc, encoders.py:53-61
+    as one op).  GSAGE_SPLIT_SELF=0: the [self | mean] tile is materialised by the gather.  Same reference outputs."""
+    monkeypatch.setenv("GSAGE_SPLIT_SELF", "1" if in_place else "0")
     g, p, x, model, enc1, enc2 = _model(name, golden)
     loss = model.train_step(list(x["nodes"]), x["labels"][x["nodes"]], lr=0.7)
     eng = model._engine
-    assert eng.split_self and eng.sets[0].comb1.shape[1] == p["f"]          # only the mean half exists
+    assert eng.split_self == in_place and eng.sets[0].comb1.shape[1] == (p["f"] if in_place else 2 * p["f"])
     assert abs(loss - float(g["loss"])) / abs(float(g["loss"])) < REL
     assert relerr(eng.gw1.cpu().numpy(), g["gw1"]) < REL
     assert relerr(enc2.weight.detach().cpu().numpy(), g["w2_new"]) < REL

@@ -43,12 +43,10 @@ for _ in range(3):
     m = ops.empty_rows(n, 602, "cuda")
     m.copy_(torch.randn(n, 602, device="cuda", generator=g))
     means.append(m)
-for pf in (0, 4):
-    os.environ["GSAGE_TC_PREFETCH"] = str(pf)
+for pf in (0,):
     tf = timed(lambda i: ops.sage_encoder_fwd_tc(table, ids, 602, means[i % 3], w, 1, h, ws=ws))
     tw = timed(lambda i: ops.sage_encoder_wgrad_tc(table, ids, 602, means[i % 3], h, gh, 1, gw, ws=ws))
     print("SAGE in-place concat, L2 prefetch %2d chunks ahead: fwd %.1f us   wgrad %.1f us" % (pf, tf, tw))
-os.environ.pop("GSAGE_TC_PREFETCH")
 for dbg in (0,):
     os.environ["GSAGE_TC_DEBUG"] = str(dbg)
     tf = timed(lambda i: ops.encoder_fwd_tc(xs[i % 3], w, 1, h, ws=ws))
@@ -62,7 +60,6 @@ os.environ["GSAGE_TC_DEBUG"] = "0"
 #   6 splitter: tcgen05.st done   7 MMA warp: operands ready   8 MMA warp: MMAs issued
 trace = torch.zeros(64 * 16, dtype=torch.int64, device="cuda")
 os.environ["GSAGE_TC_TRACE"] = str(trace.data_ptr())
-os.environ["GSAGE_TC_PREFETCH"] = "0"
 ops.sage_encoder_fwd_tc(table, ids, 602, means[0], w, 1, h, ws=ws)
 torch.cuda.synchronize()
 os.environ.pop("GSAGE_TC_TRACE")
