@@ -39,6 +39,8 @@ namespace {
 #define GS_TC_STAGES 3
 #endif
 constexpr int kStages = GS_TC_STAGES;
+static_assert(kStages == 3, "the refill duty of the splitter groups (gathered X tiles) is verified for a 3-stage ring only: "
+                            "a 4-stage build hung on the B200 in round 2");
 constexpr int kTile = 128;            // M and N of the UMMA tile (d_out == 128)
 constexpr int kChunk = 32;            // reduction elements per stage: 32 fp32 = one 128-B swizzle row
 constexpr int kOperandBytes = kTile * kChunk * 4;          // 16 KB
@@ -502,15 +504,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 }
 
 // W -> (W_hi, W_lo): the pre-split B operand of the forward GEMM (d_out x k_in, tiny)
-__global__ void split_rows_kernel(const float* __restrict__ src, int64_t ld_src, int rows, int cols,
+// columns [0, first) land at [0, first), the rest at [second_off, ...): the two 16-B aligned halves of a SAGE weight
+__global__ void split_rows_kernel(const float* __restrict__ src, int64_t ld_src, int rows, int cols, int first, int second_off,
                                   float* __restrict__ hi, float* __restrict__ lo, int64_t ld_dst) {
     const int64_t total = (int64_t)rows * cols;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(e / cols), c = (int)(e - (int64_t)r * cols);
+        const int d = c < first ? c : second_off + (c - first);
         float h, l;
         split_tf32(src[(int64_t)r * ld_src + c], h, l);
-        hi[(int64_t)r * ld_dst + c] = h;
-        lo[(int64_t)r * ld_dst + c] = l;
+        hi[(int64_t)r * ld_dst + d] = h;
+        lo[(int64_t)r * ld_dst + d] = l;
     }
 }
 
@@ -648,12 +652,8 @@ int launch_fwd(const XSource& xs, const float* w, int64_t ld_w, int32_t d_out, i
     float* w_hi = ws;
     float* w_lo = ws + (int64_t)d_out * ldw;
     GS_PREFER_SMEM(split_rows_kernel);
-    if (sc) {
-        split_rows_kernel<<<grid1d((int64_t)d_out * sc), 256, 0, s>>>(w, ld_w, d_out, sc, w_hi, w_lo, ldw);
-        GS_LAUNCH_CHECK();
-    }
-    split_rows_kernel<<<grid1d((int64_t)d_out * xs.k_dense), 256, 0, s>>>(w + sc, ld_w, d_out, xs.k_dense, w_hi + off,
-                                                                          w_lo + off, ldw);
+    split_rows_kernel<<<grid1d((int64_t)d_out * (sc + xs.k_dense)), 256, 0, s>>>(w, ld_w, d_out, sc + xs.k_dense, sc, (int)off,
+                                                                                 w_hi, w_lo, ldw);
     GS_LAUNCH_CHECK();
     CUtensorMap mx, mh, ml, msh, msl;
     int rc;
