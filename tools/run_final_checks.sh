@@ -1,3 +1,5 @@
+#!/bin/bash
+# Round-end checks on one B200 (gpurun): GPU tests, smoke, the bench line + variants, the reference arm, ncu captures.
 set -x
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4 > gpurun_out/r02_final_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_final_smoke.log 2>&1
@@ -8,3 +10,6 @@ for b in 512 4096; do timeout 600 python bench.py --steps 20 --warmup 5 --batch 
 timeout 600 python bench.py --steps 20 --warmup 5 --graph rmat --no-cpu-baseline > gpurun_out/r02_final_bench_rmat.json 2>> gpurun_out/r02_final_bench.err
 python tools/show_bench.py gpurun_out/r02_final_bench_*.json gpurun_out/r02_final_ref.json
 tail -2 gpurun_out/r02_final_pytest.log; tail -1 gpurun_out/r02_final_smoke.log
+B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
+$B > gpurun_out/ncu_plain.log 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r02_final_launches.csv $B > gpurun_out/ncu1.log 2>&1; echo rc1=$?
+$B > gpurun_out/ncu_plain2.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gather_mean_kernel|tc_gemm_kernel|head_rows_kernel" -s 4 -c 8 -o gpurun_out/r02_final_prof -f $B > gpurun_out/ncu2.log 2>&1; echo rc2=$?
