@@ -147,10 +147,11 @@ struct TcArgs {
     const int32_t* self_ids;   // [n_max] table row of every X row
     int self_units;
     int self_cols;             // feature width F (columns of the self half; the mean half follows at column F of W / dW)
-    int debug;                 // experiment switches (GSAGE_TC_DEBUG), 0 in production
+    int debug;                 // experiment switches (GSAGE_TC_DEBUG): read by the DBG instantiation only
     long long* trace;          // optional [64 chunks][16 events] clock64 trace of block 0 (GSAGE_TC_TRACE)
 };
-#define TC_TRACE(ev, c) do { if (g.trace && blockIdx.x == 0 && blockIdx.y == 0 && (c) < 64 && lane == 0) g.trace[(c) * 16 + (ev)] = clock64(); } while (0)
+// experiment hooks (stage switches, clock64 trace) exist only in the DBG instantiation; production launches the other one
+#define TC_TRACE(ev, c) do { if constexpr (DBG) { if (g.trace && blockIdx.x == 0 && blockIdx.y == 0 && (c) < 64 && lane == 0) g.trace[(c) * 16 + (ev)] = clock64(); } } while (0)
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                              uint32_t acc) {
@@ -196,7 +197,7 @@ constexpr int kBarYReady = kBarAccum + 1;         // [kStages]  Y tile split int
 //   map_x          dense part of X: the whole X, or its mean half [n, k_in] when the self half is gathered
 //   map_yhi/ylo    NT: W_hi / W_lo columns of the dense part;  TN: dZ_hi / dZ_lo
 //   map_shi/slo    NT only: W_hi / W_lo columns of the self half (columns [0, self_cols) of W)
-template <bool TN>
+template <bool TN, bool DBG>
 __global__ void __maxnreg__(72)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_yhi,
                const __grid_constant__ CUtensorMap map_ylo, const __grid_constant__ CUtensorMap map_shi,
@@ -273,7 +274,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 TC_TRACE(0, c);
                 const uint32_t st = base + s * kStageBytes;
                 const uint32_t full = bars + 8 * (kBarFull + s);
-                if ((g.debug & 8) && !gathers) { mbar_arrive(full); continue; }
+                if (DBG && (g.debug & 8) && !gathers) { mbar_arrive(full); continue; }
                 if (!TN) {
                     if (c < self_chunks) {
                         const int col = c * kChunk;
@@ -327,7 +328,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const int ks = c * (kChunk / 8) + j;       // k-step index within this CTA
                     const uint32_t d_main = tmem + (uint32_t)(ks % kMainAccs) * kTile;
                     const uint32_t acc_main = ks >= kMainAccs ? 1u : 0u, acc_corr = ks ? 1u : 0u;
-                    if (!(g.debug & 1)) {
+                    if (!(DBG && (g.debug & 1))) {
                     umma_tf32_ts(d_corr, a_lo + 8 * j, dyh, idesc, acc_corr);
                     umma_tf32_ts(d_corr, a_hi + 8 * j, dyl, idesc, 1u);
                     umma_tf32_ts(d_main, a_hi + 8 * j, dyh, idesc, acc_main);
@@ -402,7 +403,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t hi[16], lo[16];
-                if (g.debug & 2) {
+                if (DBG && (g.debug & 2)) {
 #pragma unroll
                     for (int k = 0; k < 16; ++k) { hi[k] = 0; lo[k] = 0; }
                 } else if (!TN) {
@@ -667,13 +668,15 @@ int launch_fwd(const XSource& xs, const float* w, int64_t ld_w, int32_t d_out, i
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     TcArgs g{n_max, n_dev, xs.k_dense, act, h, ld_h, 0, 0, xs.table, xs.ld_table, xs.self_ids,
              sc ? (sc + kChunk - 1) / kChunk : 0, sc, tc_debug(), tc_trace()};
-    tc_gemm_kernel<false><<<(n_max + kTile - 1) / kTile, kThreads, kSmemBytes, s>>>(mx, mh, ml, msh, msl, g);
+    if (g.debug || g.trace) tc_gemm_kernel<false, true><<<(n_max + kTile - 1) / kTile, kThreads, kSmemBytes, s>>>(mx, mh, ml, msh, msl, g);
+    else tc_gemm_kernel<false, false><<<(n_max + kTile - 1) / kTile, kThreads, kSmemBytes, s>>>(mx, mh, ml, msh, msl, g);
     GS_LAUNCH_CHECK();
     return GS_OK;
 }
@@ -704,14 +707,16 @@ int launch_wgrad(const XSource& xs, const float* h, int64_t ld_h, const float* g
     if ((rc = make_map(&ml, dz_lo, n_max, d_out, d_out, 32, kChunk, swz))) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     TcArgs g{n_max, n_dev, xs.k_dense, GS_ACT_NONE, part, ldw, rps, (int64_t)d_out * ldw, xs.table, xs.ld_table, xs.self_ids,
              self_tiles, sc, tc_debug(), nullptr};
     dim3 grid(tiles, splits);
-    tc_gemm_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(mx, mh, ml, mh, ml, g);
+    if (g.debug) tc_gemm_kernel<true, true><<<grid, kThreads, kSmemBytes, s>>>(mx, mh, ml, mh, ml, g);
+    else tc_gemm_kernel<true, false><<<grid, kThreads, kSmemBytes, s>>>(mx, mh, ml, mh, ml, g);
     GS_LAUNCH_CHECK();
     tc_reduce_kernel<<<grid1d((int64_t)d_out * k_all), 256, 0, s>>>(part, splits, (int64_t)d_out * ldw, ldw, d_out, k_all,
                                                                    gw, ld_gw);

@@ -4,7 +4,19 @@
 #include <stdint.h>
 #include "../../include/gsage.h"
 
-#define GS_NUM_SMS 148   // B200: 2 dies x 74 SMs
+// SM count of the current device (B200: 148 = 2 dies x 74), queried once; 148 when no device is visible (the sizing
+// helpers of the C ABI are callable without a GPU)
+static inline int gs_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+        else { (void)cudaGetLastError(); n = 148; }
+    }
+    return n;
+}
+#define GS_NUM_SMS gs_num_sms()
 
 #define GS_LAUNCH_CHECK()                                   \
     do {                                                    \

@@ -4,7 +4,7 @@
 UTMALDG = TMA tensor loads, SYNCS = mbarrier ops, LDG.E.128 / RED.E.ADD.F32x4-style = 128-bit loads and vector
 reductions, .SYS-scoped loads/stores = peer (NVLink) traffic.  Runs without a GPU (cuobjdump on the in-tree .so).
 
-    python tools/sass_evidence.py > profiles/r01_sass_evidence.txt
+    python tools/sass_evidence.py > profiles/r02_sass_evidence.txt
 """
 import collections
 import os
@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "graphsage-simple_b200", "graphsage", "lib", "libgsage_sm100.so")
 PATTERNS = [("tcgen05.mma", r"\bUTC\w*MMA\b"), ("tcgen05.st (A operand -> TMEM)", r"\bSTTM\b"), ("tcgen05.ld (epilogue)", r"\bLDTM\b"),
             ("tcgen05.commit", r"\bUTCBAR\b"), ("TMA tensor load", r"\bUTMALDG\b"), ("mbarrier", r"\bSYNCS\b"),
-            ("elect.sync", r"\bELECT\b"), ("128-bit global load", r"\bLDG\.E\.(?:\w+\.)*128\b"),
+            ("elect.sync", r"\bELECT\b"), ("cp.async (LDGSTS: rows gathered into the stage ring)", r"\bLDGSTS\b"), ("128-bit global load", r"\bLDG\.E\.(?:\w+\.)*128\b"),
             ("128-bit shared load", r"\bLDS\.128\b"), ("vector reduction red.v4.f32", r"\bRED\.E\.ADD\.F32x4\b|\bREDG\.E\.ADD\.F32x4\b|\bRED\.E\.ADD\.\w*F32\w*\.V?4|RED\S*128"),
             ("system-scope ld/st (.SYS: peer memory, or volatile ticket reads)", r"\b(?:LDG|STG|LD|ST)\.E\.\S*SYS\b"), ("legacy HMMA (must be 0)", r"\bHMMA\b")]
 
