@@ -392,12 +392,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if ((c + kStages) % kASlots == grp) refill(c);
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % kStages, it = c / kStages;
-            // EVERY chunk's full barrier is observed, also the other group's: a parity wait only tells phase k
-            // from phase k+1, and with an odd stage count the two groups alternate on a stage, so a group that
-            // skipped a phase could see "phase k-1 done" as "phase k+1 done" and split a tile that has not
-            // landed (measured: 3 stages, 50 % of the 26 000-row weight-gradient runs returned garbage).
-            mbar_wait(bars + 8 * (kBarFull + s), it & 1);
+            // A parity wait only tells phase k from phase k+1, and with an odd stage count the two groups alternate on a
+            // stage, so a group that asks for its own chunks' phases only could see "phase k-1 done" as "phase k+1 done"
+            // and split a tile that has not landed (measured: 3 stages, 50 % of the 26 000-row weight-gradient runs
+            // returned garbage).  Two rules keep the phase unambiguous (tools/tc_protocol_sim.py checks both):
+            //  * CTAs whose X tiles all come by TMA: EVERY chunk's full barrier is observed, also the other group's.
+            //    Between two waits such a warp only runs register / shared-memory / TMEM work, so it cannot fall a
+            //    whole ring cycle behind.
+            //  * CTAs on refill duty spend memory-latency-bound time between two waits (id loads + cp.async behind the
+            //    co-resident gather's requests), and the phase after the one a late warp is about to ask for completes
+            //    WITHOUT that warp (other group's refill + producer): lapped, its parity wait turns into a wait for a
+            //    phase that needs its own work -- a deadlock (an 8-GPU bench run hung in round 2).  They wait for their
+            //    own chunks only, and first for the stage's EMPTY barrier of chunk c - kStages: the MMAs of that chunk
+            //    waited for its full-barrier phase, and the phase after chunk c needs this warp's split of chunk c, so
+            //    the full barrier is in the phase of chunk c, pending or complete, and the parity wait is exact.  (The
+            //    producer issues chunk c only after the same empty barrier: the extra wait never delays anything.)
+            if (!gathers) mbar_wait(bars + 8 * (kBarFull + s), it & 1);
             if (c % kASlots != grp) continue;
+            if (gathers) {
+                if (c >= kStages) mbar_wait(bars + 8 * (kBarEmpty + s), (it - 1) & 1);
+                mbar_wait(bars + 8 * (kBarFull + s), it & 1);
+            }
             if (q == 2) TC_TRACE(4, c);
             const uint8_t* xs = gen_base + s * kStageBytes;
 #pragma unroll
@@ -607,7 +622,11 @@ int tc_debug() {
     return v;
 }
 long long* tc_trace() {
-    return getenv("GSAGE_TC_TRACE") ? (long long*)strtoull(getenv("GSAGE_TC_TRACE"), nullptr, 10) : nullptr;
+    static int asked = -1;       // whether the variable exists is decided once; the experiment tool may move the buffer
+    if (asked < 0) asked = getenv("GSAGE_TC_TRACE") ? 1 : 0;
+    if (!asked) return nullptr;
+    const char* e = getenv("GSAGE_TC_TRACE");
+    return e ? (long long*)strtoull(e, nullptr, 10) : nullptr;
 }
 
 int grid1d(int64_t total) {

@@ -8,6 +8,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import torch
 from graphsage import ops
 
+os.environ.setdefault("GSAGE_TC_TRACE", "0")   # the library decides once whether a trace is wanted at all; 0 = not yet
+
 n, k_in, d = 25154, 1204, 128
 g = torch.Generator(device="cuda").manual_seed(1)
 xs = []
@@ -62,7 +64,7 @@ trace = torch.zeros(64 * 16, dtype=torch.int64, device="cuda")
 os.environ["GSAGE_TC_TRACE"] = str(trace.data_ptr())
 ops.sage_encoder_fwd_tc(table, ids, 602, means[0], w, 1, h, ws=ws)
 torch.cuda.synchronize()
-os.environ.pop("GSAGE_TC_TRACE")
+os.environ["GSAGE_TC_TRACE"] = "0"
 t = trace.view(64, 16).cpu().numpy()
 t0 = t[0, 0]
 print("chunk  stage_free tma_issued | landed slot_free st_done | mma_ready mma_issued   (cycles since the first TMA wait)")
