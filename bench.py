@@ -919,8 +919,26 @@ def run_products(args):
         dist.destroy_process_group()
 
 
+def start_watchdog():
+    """A run that stops making progress (a hung kernel keeps every later CUDA call of this rank, and through the peer
+    all-reduce every other rank, waiting forever) ends with a message on stderr and exit code 3 instead of sitting in
+    cudaStreamSynchronize until some outer limit kills it.  GSAGE_BENCH_WATCHDOG_S=0 disables it."""
+    limit = float(os.environ.get("GSAGE_BENCH_WATCHDOG_S", "1500"))
+    if limit <= 0:
+        return
+
+    def fire():
+        print("bench.py: no result after %.0f s (rank %s): giving up -- a kernel or a peer rank hangs"
+              % (limit, os.environ.get("RANK", "0")), file=sys.stderr, flush=True)
+        os._exit(3)
+    t = threading.Timer(limit, fire)
+    t.daemon = True
+    t.start()
+
+
 if __name__ == "__main__":
     a = parse()
+    start_watchdog()
     if a.impl == "reference":
         run_reference(a)
     elif a.workload == "products":

@@ -23,6 +23,12 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu = False
     if has_gpu:
+        # a hung kernel must end the session with a traceback, not sit in cudaStreamSynchronize until an outer limit
+        # (the whole GPU suite runs in well under a minute); "thread": the main thread is stuck inside the driver
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(600, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
