@@ -74,7 +74,6 @@ xent_rows_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restr
     const float lse = zmax + logf(sum);
     const int y = (int)labels[row];
     float picked = 0.f;
-    float* s_dl = hrow;                               // the row's h is no longer needed below? (it is: keep separate)
     float dl[kMaxClsPerLane];
 #pragma unroll
     for (int q = 0; q < kMaxClsPerLane; ++q) {
@@ -87,7 +86,6 @@ xent_rows_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restr
             ws[(int64_t)row * C + c] = dl[q];
         }
     }
-    (void)s_dl;
 #pragma unroll
     for (int o = 16; o; o >>= 1) picked += __shfl_xor_sync(0xffffffffu, picked, o);
     if (lane == 0) ws[(int64_t)n * C + row] = lse - picked;
