@@ -57,3 +57,37 @@ def test_model_finds_the_lapping_deadlock_of_round_2(mode):
 def test_model_finds_the_parity_aliasing_of_round_1():
     bad = _failures("own_naive", "none", 200)
     assert bad and any("reads X" in b for b in bad)
+
+
+# ---- every interleaving, not a sample (tools/tc_protocol_exhaustive.py: breadth-first over the reachable states, no time)
+_spec2 = importlib.util.spec_from_file_location("tc_protocol_exhaustive", os.path.join(ROOT, "tools", "tc_protocol_exhaustive.py"))
+exh = importlib.util.module_from_spec(_spec2)
+_spec2.loader.exec_module(exh)
+
+
+@pytest.mark.parametrize("mode,n,head", [("all", 8, None), ("head", 8, 3), ("head", 7, 1), ("none", 8, None), ("all", 1, None),
+                                         ("all", 2, None), ("all", 3, None), ("head", 4, 2)])
+def test_kernel_rules_hold_under_every_interleaving(mode, n, head):
+    r = exh.explore(n, exh.mode_fn(mode, n, head), "own_only")
+    assert r["ok"] is True, r
+    # "kernel" = what gemm_tc.cu does: own_only on refill duty; TMA-only CTAs keep observe_all, which the timeless model
+    # cannot prove (it lets a warp idle between two register instructions for thousands of cycles)
+    if mode != "none":
+        assert exh.explore(n, exh.mode_fn(mode, n, head), "kernel")["ok"] is True
+
+
+def test_two_warps_per_group_named_barrier_and_skew():
+    assert exh.explore(3, exh.mode_fn("all", 3), "kernel", wpg=2)["ok"] is True        # 4+ chunks: tools/, minutes
+
+
+def test_exhaustive_search_finds_the_round_2_deadlock_with_a_shortest_schedule():
+    r = exh.explore(4, exh.mode_fn("all", 4), "observe_all")
+    assert r["ok"] is False and "deadlock" in r["why"]
+    # the late group is the one that has to issue TWO refills before its first wait (chunks 0 and 2): it is lapped on
+    # stage 0, whose next phase (chunk 3) completes without it
+    assert any("('wait', 'F', 0, 0)" in w for w in [r["why"]])
+
+
+def test_exhaustive_search_finds_the_round_1_aliasing():
+    r = exh.explore(6, exh.mode_fn("none", 6), "own_naive")
+    assert r["ok"] is False and "reads X" in r["why"]
