@@ -17,9 +17,10 @@
 // version of this kernel (profiles/README.md, r01 tc_gemm v1 vs v2).
 //
 // SAGE concat in place (graphsage/encoders.py:53-56 `cat([self.features(nodes), neigh_feats])`): when X is
-// [table[self_ids] | mean], only the mean half exists in memory; the producer warp gathers the self rows straight
-// from the feature table with coalesced 16-B cp.async (LDGSTS) into the same swizzled stage ring, so the self half of
-// the combined tile is never written or re-read through HBM (gs_sage_encoder_fwd_tc / gs_sage_encoder_wgrad_tc).
+// [table[self_ids] | mean], only the mean half exists in memory; the self rows are gathered straight from the feature
+// table with coalesced 16-B cp.async (LDGSTS) into the same swizzled stage ring -- by the splitter group that just
+// freed the stage's X region ("refill duty", below) -- so the self half of the combined tile is never written or
+// re-read through HBM (gs_sage_encoder_fwd_tc / gs_sage_encoder_wgrad_tc; the engine's default in SAGE mode).
 //
 // Per CTA (320 threads, 1 CTA/SM): 3-stage smem ring of 48 KB (X raw, Y_hi, Y_lo), TMEM =
 // 2 main accumulators + 1 correction accumulator (3 x 128 columns) + 2 A slots (2 x 64 columns).
@@ -39,8 +40,8 @@ namespace {
 #define GS_TC_STAGES 3
 #endif
 constexpr int kStages = GS_TC_STAGES;
-static_assert(kStages == 3, "the refill duty of the splitter groups (gathered X tiles) is verified for a 3-stage ring only: "
-                            "a 4-stage build hung on the B200 in round 2");
+static_assert(kStages == 3, "the splitter groups' wait rules and refill duty are verified (GPU tests, protocol model) for a "
+                            "3-stage ring only");
 constexpr int kTile = 128;            // M and N of the UMMA tile (d_out == 128)
 constexpr int kChunk = 32;            // reduction elements per stage: 32 fp32 = one 128-B swizzle row
 constexpr int kOperandBytes = kTile * kChunk * 4;          // 16 KB
@@ -86,10 +87,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
 }
 // Gathered feature rows: 16-B cp.async (LDGSTS, L2-only) straight into the stage, completion counted on the stage's
-// full barrier; src_bytes = 0 zero-fills the 16 bytes.  Measured (profiles/README.md, round 2): one issuing warp pays
+// full barrier; src_bytes = 0 zero-fills the 16 bytes.  Measured (profiles/README.md R2.3): one issuing warp pays
 // ~45-50 cycles per LDGSTS (32 per chunk = the whole chunk period) and ~55 cycles per 1-D bulk copy (UBLKCP; 128 per
-// chunk made the forward 2.9x slower), so the in-place concat is correct but SLOWER than reading a materialised tile:
-// it stays an option (GSAGE_SPLIT_SELF=1), not the default.
+// chunk made the forward 2.9x slower), so the copies are issued by the 128 threads of a splitter group, 8 each.
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes));
 }
@@ -139,9 +139,9 @@ struct TcArgs {
     int64_t ld_out;
     int rows_per_split;        // TN only (multiple of kChunk)
     int64_t split_stride;      // TN only
-    // SAGE concat consumed in place: X = [table[self_ids] | mean].  The self half is never materialised: the
-    // producer warp gathers the rows straight from the feature table (graphsage/encoders.py:53 `self.features(nodes)`
-    // + the cat of :56) with 1-D bulk copies.  NT: the first self_units K chunks; TN: the first self_units column tiles.
+    // SAGE concat consumed in place: X = [table[self_ids] | mean].  The self half is never materialised: the rows
+    // are gathered straight from the feature table (graphsage/encoders.py:53 `self.features(nodes)` + the cat of :56)
+    // by the splitter groups' refill duty.  NT: the first self_units K chunks; TN: the first self_units column tiles.
     const float* table;        // nullptr: X is one dense matrix (map_x), self_units == 0
     int64_t ld_table;
     const int32_t* self_ids;   // [n_max] table row of every X row
@@ -395,7 +395,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             // A parity wait only tells phase k from phase k+1, and with an odd stage count the two groups alternate on a
             // stage, so a group that asks for its own chunks' phases only could see "phase k-1 done" as "phase k+1 done"
             // and split a tile that has not landed (measured: 3 stages, 50 % of the 26 000-row weight-gradient runs
-            // returned garbage).  Two rules keep the phase unambiguous (tools/tc_protocol_sim.py checks both):
+            // returned garbage).  Two rules keep the phase unambiguous (tools/tc_protocol_sim.py, tc_protocol_exhaustive.py):
             //  * CTAs whose X tiles all come by TMA: EVERY chunk's full barrier is observed, also the other group's.
             //    Between two waits such a warp only runs register / shared-memory / TMEM work, so it cannot fall a
             //    whole ring cycle behind.
