@@ -221,7 +221,7 @@ def encoder_wgrad_tc(x, h, gh, act, gw, ws=None, n_dev=None):
 
 def sage_encoder_fwd_tc(table, self_ids, feat_dim, mean, w, act, h, ws=None, n_dev=None):
     """h = act([table[self_ids] | mean] . w^T) on tcgen05; the self rows are gathered from the table inside the
-    GEMM's producer (the self half of the combined tile is never materialised) -- see gs_sage_encoder_fwd_tc."""
+    GEMM (the self half of the combined tile is never materialised) -- see gs_sage_encoder_fwd_tc."""
     lib = N.load()
     N.require_cuda(table, self_ids, mean, w, h)
     n_max, d_out = mean.shape[0], w.shape[0]

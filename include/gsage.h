@@ -166,9 +166,9 @@ GS_API int gs_encoder_fwd_tc(const float* x, int64_t ld_x, const float* w, int64
 /* SAGE concat consumed in place (encoders.py:49-61 as ONE op for the rows of the feature table):
  *   h = act([table[self_ids] | mean] . w^T)          w [d_out, 2 * feat_dim] = [W_self | W_neigh]
  * `mean` [n, feat_dim] is the neighbour mean gs_gather_mean_fwd wrote (self_ids == NULL, neigh_off == 0); the self
- * half of the combined tile is NOT materialised: the GEMM's producer warp gathers the rows `self.features(nodes)`
- * (encoders.py:53) straight from the table into its shared-memory stage ring, and the tcgen05 MMAs consume them
- * there.  gs_sage_encoder_wgrad_tc is the matching weight gradient gw [d_out, 2 * feat_dim] = dz^T . [table[self_ids] | mean].
+ * half of the combined tile is NOT materialised: the GEMM's splitter warps gather the rows `self.features(nodes)`
+ * (encoders.py:53) straight from the table into the shared-memory stage ring (cp.async into the stage region they
+ * just freed), and the tcgen05 MMAs consume them from there.  gs_sage_encoder_wgrad_tc is the matching weight gradient gw [d_out, 2 * feat_dim] = dz^T . [table[self_ids] | mean].
  * ws sizes: gs_encoder_fwd_tc_ws_floats(2 * feat_dim, d_out), gs_encoder_wgrad_tc_ws_floats(n_max, 2 * feat_dim, d_out). */
 GS_API int gs_sage_encoder_fwd_tc(const float* table, int64_t ld_table, const int32_t* self_ids, int32_t feat_dim,
                            const float* mean, int64_t ld_mean, const float* w, int64_t ld_w,
