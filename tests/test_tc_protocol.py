@@ -91,3 +91,13 @@ def test_exhaustive_search_finds_the_round_2_deadlock_with_a_shortest_schedule()
 def test_exhaustive_search_finds_the_round_1_aliasing():
     r = exh.explore(6, exh.mode_fn("none", 6), "own_naive")
     assert r["ok"] is False and "reads X" in r["why"]
+
+
+def test_model_reproduces_the_four_stage_history(monkeypatch):
+    """Round 1: with FOUR stages each group always meets the same stages, so waiting for own chunks only was sound (0 / 60
+    bad runs on the B200) -- it is the odd ring that aliased.  Round 2: four stages + refill duty + observe-everything
+    hung on the B200.  The model says the same three things."""
+    monkeypatch.setattr(exh, "S", 4)
+    assert exh.explore(9, exh.mode_fn("none", 9), "own_naive")["ok"] is True
+    assert exh.explore(9, exh.mode_fn("all", 9), "observe_all")["ok"] is False
+    assert exh.explore(9, exh.mode_fn("none", 9), "own_only")["ok"] is True

@@ -270,10 +270,13 @@ def main():
     ap.add_argument("--head", type=int, default=None, help="mode head: number of gathered chunks")
     ap.add_argument("--wpg", type=int, default=1, help="warps per splitter group in the model")
     ap.add_argument("--trace", action="store_true")
+    ap.add_argument("--stages", type=int, default=3, help="ring depth (the kernel is built with 3)")
     args = ap.parse_args()
+    global S
+    S = args.stages
     r = explore(args.chunks, mode_fn(args.mode, args.chunks, args.head), args.rule, args.wpg)
-    print("rule %s, X gathered: %s, %d chunks, %d warp(s)/group: %s after %d states%s"
-          % (args.rule, args.mode, args.chunks, args.wpg, {True: "ALL SCHEDULES OK", False: "VIOLATION", None: "inconclusive"}[r["ok"]],
+    print("rule %s, %d stages, X gathered: %s, %d chunks, %d warp(s)/group: %s after %d states%s"
+          % (args.rule, S, args.mode, args.chunks, args.wpg, {True: "ALL SCHEDULES OK", False: "VIOLATION", None: "inconclusive"}[r["ok"]],
              r["states"], "" if r["ok"] else ": " + r["why"]))
     if args.trace and r.get("trace"):
         for t in r["trace"]:
