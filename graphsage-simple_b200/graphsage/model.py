@@ -220,9 +220,12 @@ class StreamTrainer:
             self.variants, self.busy = cache[k]
         v = self.turn
         self.turn ^= 1
+        blocks, losses = self.variants[v]
         if self.busy[v] is not None:
             self.busy[v].synchronize()             # the launch that last read these pinned buffers has finished
-        blocks, losses = self.variants[v]
+            for h in self.fifo:                    # its losses that nobody has asked for yet: read them out before the
+                if isinstance(h, _HostLoss) and h._buf is losses and h._value is None:      # new launch overwrites them
+                    h._value = float(losses[h._j])
         for j, blk in enumerate(self.pending[:k]):
             blocks[j].copy_(blk)
         del self.pending[:k]
